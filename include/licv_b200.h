@@ -1,0 +1,208 @@
+/*
+ * licv_b200.h - C ABI of the B200-native L-ICV hot path (liblicv_b200.so, sm_100a only).
+ *
+ * Drop-in boundary for ForJadeForest/LICV-VQA's data-parallel hot path.  The reference is pure
+ * Python; what crosses its "FFI" for this path are torch tensors handed to the forward hooks of
+ * `LearnableICVInterventionLMM` and to `VQAICVModule.calculate_kl_divergence`.  Every entry point
+ * below names the reference code it replaces (paths relative to the reference root).  Signatures
+ * carry plain pointers and sizes only - no torch types.  The Python host side
+ * (licv_vqa_b200/_abi.py) binds them with ctypes; INTEGRATION.md shows the stub a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the function name ends in `_host`;
+ *  - tensors are row-major and contiguous in the last dimension; rows must start on a 16-byte
+ *    boundary for the injection kernels (d % 8 == 0 for bf16/fp16, d % 4 == 0 for fp32); the loss
+ *    kernels accept any V and any element-aligned row stride (V = 32002 / 32003 are the cases);
+ *  - work is enqueued on `stream` and the call returns without synchronising; no allocation
+ *    happens inside any non-`_host` call (workspaces are passed in);
+ *  - return value: 0 = LICV_OK, otherwise a negative licv_status (argument errors, reported
+ *    before anything is launched) or a positive cudaError_t from the launch;
+ *  - there is NO CPU path: the library needs a device of compute capability 10.x.
+ */
+#ifndef LICV_B200_H_
+#define LICV_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LICV_ABI_VERSION 1
+
+typedef struct CUstream_st* licv_stream_t; /* == cudaStream_t */
+
+typedef enum {
+    LICV_OK = 0,
+    LICV_ERR_NULL_POINTER = -1,
+    LICV_ERR_BAD_DTYPE = -2,
+    LICV_ERR_BAD_DIM = -3,        /* d not a multiple of the 16-byte vector, or too large */
+    LICV_ERR_MISALIGNED = -4,     /* base pointer not 16-byte aligned */
+    LICV_ERR_BAD_ARGUMENT = -5,
+    LICV_ERR_WORKSPACE = -6,      /* workspace too small */
+    LICV_ERR_NO_DEVICE = -7       /* no sm_100 device / kernel image not loadable */
+} licv_status;
+
+typedef enum { LICV_F32 = 0, LICV_BF16 = 1, LICV_F16 = 2 } licv_dtype;
+
+/* Where the reference's eager op chain rounds when hidden states are bf16/fp16
+ * (icv_src/icv_model/icv_intervention.py:66-72 under torch type promotion / CUDA autocast).
+ * 0 = all arithmetic in fp32, one rounding at the output. */
+#define LICV_ROUND_Y 1u   /* `hidden_states + shift` stored in low precision (shift is low precision) */
+#define LICV_ROUND_NH 2u  /* `hidden_states.norm()` stored in low precision (no autocast) */
+#define LICV_ROUND_NY 4u  /* `shifted_states.norm()` stored in low precision */
+#define LICV_ROUND_T 8u   /* `shifted_states / norm` stored in low precision */
+/* loss kernel: `logits /= temperature` (icv_src/icv_module.py:122-123) stores the quotient in the
+ * logits' own low-precision dtype before the fp32 softmax */
+#define LICV_ROUND_TEMPERED 16u
+
+const char* licv_status_string(int status);
+int licv_abi_version(void);
+/* SM count / compute capability of the current device; LICV_ERR_NO_DEVICE if it is not sm_10x. */
+int licv_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * a1+a2  icv = get_alpha().unsqueeze(-1) * in_context_vector
+ *   replaces GlobalICVEncoder.get_alpha (icv_src/icv_encoder/global_icv_encoder.py:40-43) and the
+ *   product at icv_src/icv_module.py:89-92 / inference.py:311.
+ *   alpha_raw [L], vec [L,d] -> icv [L,d] (all fp32).  use_sigmoid != 0 applies sigmoid first.
+ * ------------------------------------------------------------------------------------------ */
+int licv_icv_scale(const float* alpha_raw, const float* vec, float* icv, int n_layers, int d,
+                   int use_sigmoid, licv_stream_t stream);
+
+/* autograd of the above: d_icv [L,d] -> d_vec [L,d] = alpha_eff * d_icv,
+ * d_alpha_raw [L] = (d_icv . vec) * (sigmoid' if use_sigmoid).  d_alpha_raw may be NULL
+ * (alpha_learnable = False, global_icv_encoder.py:26-29). */
+int licv_icv_scale_bwd(const float* alpha_raw, const float* vec, const float* d_icv, float* d_vec,
+                       float* d_alpha_raw, int n_layers, int d, int use_sigmoid,
+                       licv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a3  residual-stream injection, forward
+ *   replaces intervention_function (icv_src/icv_model/icv_intervention.py:61-86), the body of
+ *   the baukit TraceDict hook:  out = (h + s) / ||h + s||_2 * ||h||_2   per token, no eps.
+ *   h [n_tokens, d] (h_dtype), shift [d] fp32 (= icv[0, layer_to_icv_index[layer]]),
+ *   out [n_tokens, d] (out_dtype: h_dtype, or LICV_F32 = the reference's promoted result).
+ *   round_flags: LICV_ROUND_* (ignored for fp32 h).  out may not alias h.
+ * ------------------------------------------------------------------------------------------ */
+int licv_inject_fwd(const void* h, const float* shift, void* out, int64_t n_tokens, int d,
+                    int h_dtype, int out_dtype, unsigned round_flags, licv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a4  residual-stream injection, backward (the reference gets this from autograd)
+ *   g [n_tokens, d] (g_dtype = the forward's out_dtype) -> dh [n_tokens, d] (h_dtype) and
+ *   d_shift [d] fp32, ACCUMULATED (+=) over all tokens with fp32 atomics: zero it first.
+ *   dh may alias g when g_dtype == h_dtype.  dh may be NULL (frozen input, only d_shift wanted).
+ * ------------------------------------------------------------------------------------------ */
+int licv_inject_bwd(const void* h, const void* g, const float* shift, void* dh, float* d_shift,
+                    int64_t n_tokens, int d, int h_dtype, int g_dtype, unsigned round_flags,
+                    licv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a6  VQAICVModule.get_mask (icv_src/icv_module.py:136-148)
+ *   mask[b,t] = (t >= mask_length[b]) && (input_ids[b,t] != pad_token_id), uint8 0/1 (torch.bool)
+ * ------------------------------------------------------------------------------------------ */
+int licv_get_mask(const int64_t* input_ids, const int64_t* mask_length, int64_t pad_token_id,
+                  int batch, int seq_len, uint8_t* mask, licv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a6+a7 (+ label prep of a9)  row selection without materialising gathered copies
+ *   replaces the two get_mask calls and the boolean-mask gathers at icv_src/icv_module.py:84-85,
+ *   108-111, and the shifted-label construction of the HF CE consumed at :94-98.
+ *   The n-th selected student row (row-major over [B,Tq]) is paired with the n-th selected teacher
+ *   row (row-major over [B,Tt]).
+ *     kl_tea_row [B*Tq] int32 : flat teacher row for each student row, -1 = not a KL row
+ *     ce_label   [B*Tq] int64 : next-token label, -100 = not a CE row (may be NULL)
+ *     counts     [4]    int32 : {N = KL rows, M = CE rows, teacher rows selected, 0}
+ *   ce_variant: 0 "idefics" (transformers 4.38.2: keep rows with attention_mask[b,t+1] != 0),
+ *               1 "idefics2" (same and label != image_token_id), 2 "causal_lm" (transformers 5.x
+ *               ForCausalLMLoss: every shifted position).  stu_attention_mask may be NULL
+ *               (treated as all ones).  counts[0] != counts[2] is the reference's shape error;
+ *               the host side checks it.
+ * ------------------------------------------------------------------------------------------ */
+int licv_kd_prepare_rows(const int64_t* stu_ids, const int64_t* stu_mask_length,
+                         const int64_t* stu_attention_mask, const int64_t* tea_ids,
+                         const int64_t* tea_mask_length, int64_t pad_token_id,
+                         int64_t image_token_id, int ce_variant, int batch, int stu_len,
+                         int tea_len, int32_t* kl_tea_row, int64_t* ce_label, int32_t* counts,
+                         licv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a7+a8+a9+a10  distillation loss, forward + backward in one pass over HBM
+ *   replaces VQAICVModule.calculate_kl_divergence (icv_src/icv_module.py:121-134), the HF-internal
+ *   shifted cross-entropy consumed at :94-98,115-117 and the combine at :100-101,107-119.
+ *
+ *   stu  [R, V] student logits, row stride stu_stride elements
+ *   dstu [R, V] receives d loss / d stu (same dtype/stride); MAY ALIAS stu (in place); rows that
+ *        are neither KL nor CE rows are zero-filled.  NULL = loss only.
+ *   tea  [Rt, V] teacher logits, row stride tea_stride (rows addressed through kl_tea_row)
+ *   kl_tea_row [R] int32 or NULL (NULL = row r pairs with teacher row r: the compact [N,V] form
+ *        `calculate_kl_divergence` itself takes)
+ *   ce_label [R] int64 or NULL (no CE term)
+ *   counts: device int32 {N, M} as written by licv_kd_prepare_rows, or NULL to use the host
+ *        values n_kl / n_ce
+ *   loss = T^2/N * sum_rows KL + hard_loss_weight * (1/M) * sum_rows CE;  only_hard_loss != 0
+ *        returns the CE alone (icv_module.py:100-101).  CE uses the un-tempered logits.
+ *   grad_scale multiplies dstu (1.0, or 1/accumulate_grad_batches).
+ *   out_losses [3] fp32 device: {kl_loss, ce_loss, loss}.
+ *   workspace: licv_kd_loss_workspace_bytes(R) bytes, 16-byte aligned; its first 16 bytes must be
+ *        zero before the first use (the kernel leaves them zero again).
+ * ------------------------------------------------------------------------------------------ */
+int64_t licv_kd_loss_workspace_bytes(int64_t n_rows);
+int licv_kd_loss_fwd_bwd(const void* stu, void* dstu, const void* tea, const int32_t* kl_tea_row,
+                         const int64_t* ce_label, const int32_t* counts, int64_t n_kl, int64_t n_ce,
+                         float temperature, float kl_eps, float hard_loss_weight,
+                         int only_hard_loss, float grad_scale, float* out_losses, void* workspace,
+                         int64_t n_rows, int vocab, int64_t stu_stride, int64_t tea_stride,
+                         int dtype, unsigned round_flags, licv_stream_t stream);
+
+/* x[i] *= *scale for i < n, skipped entirely (no traffic) when *scale == 1: the upstream
+ * gradient of the loss applied to the in-place dstu in the autograd backward. */
+int licv_scale_inplace(void* x, int64_t n, const float* scale, int dtype, licv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * f2 ("next" row)  optimizer step on the flat ICV parameter buffer
+ *   replaces torch.optim.AdamW / DeepSpeedCPUAdam + gradient_clip_val + the cosine warm-up
+ *   schedule (icv_src/icv_module.py:171-209, config/trainer/*.yaml) for the L*d + L trainable
+ *   floats.  flat layout: [vec (n_vec floats) | alpha (n_alpha floats)].
+ *   grad is first multiplied by grad_prescale (1/world_size after the all-reduce sum), then
+ *   clipped to global L2 norm max_grad_norm (<= 0 disables), then AdamW with lr_vec / lr_alpha.
+ *   step counts from 1.  norm_out [1] fp32 device receives the pre-clip gradient norm (or NULL).
+ * ------------------------------------------------------------------------------------------ */
+int licv_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                    int64_t n_vec, int64_t n_alpha, float lr_vec, float lr_alpha, float beta1,
+                    float beta2, float eps, float weight_decay, int64_t step, float grad_prescale,
+                    float max_grad_norm, float* norm_out, void* workspace /* >= 16 B, zeroed */,
+                    licv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-buffer entry points (what a host-side plugin of the reference would call): inputs and
+ * outputs live in HOST memory (pinned memory makes the copies asynchronous); the call stages
+ * them through device scratch owned by the session, runs the same kernels and copies the
+ * results back.  Calls on one session are pipelined on internal streams (copy-in of call k+1
+ * overlaps the kernel of call k and the copy-out of call k-1); licv_host_sync waits for all.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct licv_host_session licv_host_session;
+int licv_host_session_create(licv_host_session** out, int64_t scratch_bytes_per_slot, int n_slots);
+int licv_host_session_destroy(licv_host_session* s);
+int licv_host_sync(licv_host_session* s);
+void* licv_host_alloc_pinned(int64_t bytes);
+void licv_host_free_pinned(void* p);
+
+int licv_inject_fwd_host(licv_host_session* s, const void* h, const float* shift, void* out,
+                         int64_t n_tokens, int d, int h_dtype, int out_dtype, unsigned round_flags);
+int licv_inject_bwd_host(licv_host_session* s, const void* h, const void* g, const float* shift,
+                         void* dh, float* d_shift /* [d], overwritten */, int64_t n_tokens, int d,
+                         int h_dtype, int g_dtype, unsigned round_flags);
+int licv_kd_loss_fwd_bwd_host(licv_host_session* s, const void* stu, void* dstu, const void* tea,
+                              const int32_t* kl_tea_row, const int64_t* ce_label, int64_t n_kl,
+                              int64_t n_ce, float temperature, float kl_eps, float hard_loss_weight,
+                              int only_hard_loss, float grad_scale, float* out_losses /* host [3] */,
+                              int64_t n_rows, int64_t n_tea_rows, int vocab, int dtype,
+                              unsigned round_flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LICV_B200_H_ */

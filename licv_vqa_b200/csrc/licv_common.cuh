@@ -1,0 +1,173 @@
+// Shared device helpers for the L-ICV hot-path kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "licv_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "liblicv_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace licv {
+
+constexpr int kWarp = 32;
+
+// ---------------------------------------------------------------------------------------------
+// storage formats
+// ---------------------------------------------------------------------------------------------
+template <int DT> struct Fmt;
+template <> struct Fmt<LICV_F32> {
+    static constexpr int kBytes = 4;
+    static constexpr int kPerVec = 4;  // elements per 16-byte vector
+    __device__ static __forceinline__ float round(float x) { return x; }
+};
+template <> struct Fmt<LICV_BF16> {
+    static constexpr int kBytes = 2;
+    static constexpr int kPerVec = 8;
+    __device__ static __forceinline__ float round(float x) {
+        return __bfloat162float(__float2bfloat16_rn(x));
+    }
+};
+template <> struct Fmt<LICV_F16> {
+    static constexpr int kBytes = 2;
+    static constexpr int kPerVec = 8;
+    __device__ static __forceinline__ float round(float x) {
+        return __half2float(__float2half_rn(x));
+    }
+};
+
+// unpack one 16-byte vector into fp32 lanes
+template <int DT> __device__ __forceinline__ void unpack(const uint4& v, float* f);
+template <> __device__ __forceinline__ void unpack<LICV_F32>(const uint4& v, float* f) {
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
+    f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+}
+template <> __device__ __forceinline__ void unpack<LICV_BF16>(const uint4& v, float* f) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // bf16 -> fp32 is a 16-bit shift
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+template <> __device__ __forceinline__ void unpack<LICV_F16>(const uint4& v, float* f) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 p = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        f[2 * i] = p.x;
+        f[2 * i + 1] = p.y;
+    }
+}
+
+// pack fp32 lanes into one 16-byte vector (round-to-nearest-even)
+template <int DT> __device__ __forceinline__ uint4 pack(const float* f);
+template <> __device__ __forceinline__ uint4 pack<LICV_F32>(const float* f) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                      __float_as_uint(f[3]));
+}
+template <> __device__ __forceinline__ uint4 pack<LICV_BF16>(const float* f) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&p);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+template <> __device__ __forceinline__ uint4 pack<LICV_F16>(const float* f) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 p = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&p);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// scalar element load/store
+template <int DT> __device__ __forceinline__ float load_elem(const void* base, int64_t i);
+template <> __device__ __forceinline__ float load_elem<LICV_F32>(const void* b, int64_t i) {
+    return static_cast<const float*>(b)[i];
+}
+template <> __device__ __forceinline__ float load_elem<LICV_BF16>(const void* b, int64_t i) {
+    return __bfloat162float(static_cast<const __nv_bfloat16*>(b)[i]);
+}
+template <> __device__ __forceinline__ float load_elem<LICV_F16>(const void* b, int64_t i) {
+    return __half2float(static_cast<const __half*>(b)[i]);
+}
+template <int DT> __device__ __forceinline__ void store_elem(void* base, int64_t i, float x);
+template <> __device__ __forceinline__ void store_elem<LICV_F32>(void* b, int64_t i, float x) {
+    static_cast<float*>(b)[i] = x;
+}
+template <> __device__ __forceinline__ void store_elem<LICV_BF16>(void* b, int64_t i, float x) {
+    static_cast<__nv_bfloat16*>(b)[i] = __float2bfloat16_rn(x);
+}
+template <> __device__ __forceinline__ void store_elem<LICV_F16>(void* b, int64_t i, float x) {
+    static_cast<__half*>(b)[i] = __float2half_rn(x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 128-bit global memory access
+// ---------------------------------------------------------------------------------------------
+// streaming read of data that is touched once: read-only path, do not allocate in L1
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+// plain coherent read (used when the destination may alias the source)
+__device__ __forceinline__ uint4 ld_plain(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p)
+                 : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_vec(uint4* p, const uint4& v) {
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+// fp32x4 reduction into global memory (one REDG.F32x4, no return value)
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
+                 "f"(d)
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
+
+// device properties, cached per device
+struct DeviceInfo {
+    int sm_count = 0;
+    int cc_major = 0;
+    int cc_minor = 0;
+    int status = LICV_ERR_NO_DEVICE;
+};
+const DeviceInfo& device_info();
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace licv

@@ -1,0 +1,202 @@
+// Host-buffer entry points: the calls a host-side plugin makes when its tensors live in host
+// memory.  A session owns n_slots (device scratch, stream) pairs; call k runs entirely on slot
+// k % n_slots, so the copy-in of one call overlaps the kernel of the previous one and the
+// copy-out of the one before.  Pinned host buffers make the copies truly asynchronous.
+#include <new>
+#include <vector>
+
+#include "licv_common.cuh"
+
+struct licv_host_session {
+    struct Slot {
+        char* scratch = nullptr;
+        cudaStream_t stream = nullptr;
+    };
+    std::vector<Slot> slots;
+    int64_t bytes = 0;
+    uint64_t next = 0;
+};
+
+namespace {
+
+// bump allocator over one slot's scratch, 256-byte granules
+struct Carver {
+    char* base;
+    int64_t cap;
+    int64_t off = 0;
+    bool ok = true;
+    void* take(int64_t bytes) {
+        const int64_t a = (off + 255) & ~int64_t(255);
+        if (a + bytes > cap) {
+            ok = false;
+            return nullptr;
+        }
+        off = a + bytes;
+        return base + a;
+    }
+};
+
+inline int64_t esize(int dtype) { return dtype == LICV_F32 ? 4 : 2; }
+
+licv_host_session::Slot* acquire(licv_host_session* s) {
+    auto* slot = &s->slots[s->next++ % s->slots.size()];
+    // the slot's previous call (n_slots calls ago) must have drained before its scratch is reused
+    cudaStreamSynchronize(slot->stream);
+    return slot;
+}
+
+#define LICV_CUDA(x)                                   \
+    do {                                               \
+        cudaError_t e__ = (x);                         \
+        if (e__ != cudaSuccess) return (int)e__;       \
+    } while (0)
+
+}  // namespace
+
+extern "C" int licv_host_session_create(licv_host_session** out, int64_t scratch_bytes_per_slot,
+                                        int n_slots) {
+    if (!out) return LICV_ERR_NULL_POINTER;
+    if (scratch_bytes_per_slot <= 0 || n_slots < 1 || n_slots > 16) return LICV_ERR_BAD_ARGUMENT;
+    if (licv::device_info().status != LICV_OK) return licv::device_info().status;
+    auto* s = new (std::nothrow) licv_host_session();
+    if (!s) return LICV_ERR_BAD_ARGUMENT;
+    s->bytes = scratch_bytes_per_slot;
+    s->slots.resize(n_slots);
+    for (auto& slot : s->slots) {
+        cudaError_t e = cudaMalloc(&slot.scratch, (size_t)scratch_bytes_per_slot);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&slot.stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            licv_host_session_destroy(s);
+            return (int)e;
+        }
+    }
+    *out = s;
+    return LICV_OK;
+}
+
+extern "C" int licv_host_session_destroy(licv_host_session* s) {
+    if (!s) return LICV_OK;
+    for (auto& slot : s->slots) {
+        if (slot.stream) {
+            cudaStreamSynchronize(slot.stream);
+            cudaStreamDestroy(slot.stream);
+        }
+        if (slot.scratch) cudaFree(slot.scratch);
+    }
+    delete s;
+    return LICV_OK;
+}
+
+extern "C" int licv_host_sync(licv_host_session* s) {
+    if (!s) return LICV_ERR_NULL_POINTER;
+    for (auto& slot : s->slots) LICV_CUDA(cudaStreamSynchronize(slot.stream));
+    return LICV_OK;
+}
+
+extern "C" void* licv_host_alloc_pinned(int64_t bytes) {
+    void* p = nullptr;
+    if (bytes <= 0 || cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void licv_host_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" int licv_inject_fwd_host(licv_host_session* s, const void* h, const float* shift,
+                                    void* out, int64_t n_tokens, int d, int h_dtype, int out_dtype,
+                                    unsigned round_flags) {
+    if (!s) return LICV_ERR_NULL_POINTER;
+    if (n_tokens < 0 || d <= 0) return LICV_ERR_BAD_ARGUMENT;
+    if (n_tokens == 0) return LICV_OK;
+    if (!h || !shift || !out) return LICV_ERR_NULL_POINTER;
+    auto* slot = acquire(s);
+    Carver c{slot->scratch, s->bytes};
+    const int64_t hb = n_tokens * d * esize(h_dtype), ob = n_tokens * d * esize(out_dtype);
+    void* dh = c.take(hb);
+    float* ds = static_cast<float*>(c.take((int64_t)d * 4));
+    void* dout = c.take(ob);
+    if (!c.ok) return LICV_ERR_WORKSPACE;
+    LICV_CUDA(cudaMemcpyAsync(dh, h, (size_t)hb, cudaMemcpyHostToDevice, slot->stream));
+    LICV_CUDA(cudaMemcpyAsync(ds, shift, (size_t)d * 4, cudaMemcpyHostToDevice, slot->stream));
+    if (int rc = licv_inject_fwd(dh, ds, dout, n_tokens, d, h_dtype, out_dtype, round_flags,
+                                 reinterpret_cast<licv_stream_t>(slot->stream)))
+        return rc;
+    LICV_CUDA(cudaMemcpyAsync(out, dout, (size_t)ob, cudaMemcpyDeviceToHost, slot->stream));
+    return LICV_OK;
+}
+
+extern "C" int licv_inject_bwd_host(licv_host_session* s, const void* h, const void* g,
+                                    const float* shift, void* dh_out, float* d_shift,
+                                    int64_t n_tokens, int d, int h_dtype, int g_dtype,
+                                    unsigned round_flags) {
+    if (!s) return LICV_ERR_NULL_POINTER;
+    if (n_tokens < 0 || d <= 0) return LICV_ERR_BAD_ARGUMENT;
+    if (!d_shift) return LICV_ERR_NULL_POINTER;
+    if (n_tokens > 0 && (!h || !g || !shift)) return LICV_ERR_NULL_POINTER;
+    auto* slot = acquire(s);
+    Carver c{slot->scratch, s->bytes};
+    const int64_t hb = n_tokens * d * esize(h_dtype), gb = n_tokens * d * esize(g_dtype);
+    void* dh = c.take(hb);
+    void* dg = c.take(gb);
+    float* ds = static_cast<float*>(c.take((int64_t)d * 4));
+    float* dds = static_cast<float*>(c.take((int64_t)d * 4));
+    void* ddh = dh_out ? c.take(hb) : nullptr;
+    if (!c.ok) return LICV_ERR_WORKSPACE;
+    LICV_CUDA(cudaMemsetAsync(dds, 0, (size_t)d * 4, slot->stream));
+    if (n_tokens > 0) {
+        LICV_CUDA(cudaMemcpyAsync(dh, h, (size_t)hb, cudaMemcpyHostToDevice, slot->stream));
+        LICV_CUDA(cudaMemcpyAsync(dg, g, (size_t)gb, cudaMemcpyHostToDevice, slot->stream));
+        LICV_CUDA(cudaMemcpyAsync(ds, shift, (size_t)d * 4, cudaMemcpyHostToDevice, slot->stream));
+        if (int rc = licv_inject_bwd(dh, dg, ds, ddh, dds, n_tokens, d, h_dtype, g_dtype,
+                                     round_flags, reinterpret_cast<licv_stream_t>(slot->stream)))
+            return rc;
+        if (dh_out)
+            LICV_CUDA(cudaMemcpyAsync(dh_out, ddh, (size_t)hb, cudaMemcpyDeviceToHost, slot->stream));
+    }
+    LICV_CUDA(cudaMemcpyAsync(d_shift, dds, (size_t)d * 4, cudaMemcpyDeviceToHost, slot->stream));
+    return LICV_OK;
+}
+
+extern "C" int licv_kd_loss_fwd_bwd_host(licv_host_session* s, const void* stu, void* dstu,
+                                         const void* tea, const int32_t* kl_tea_row,
+                                         const int64_t* ce_label, int64_t n_kl, int64_t n_ce,
+                                         float temperature, float kl_eps, float hard_loss_weight,
+                                         int only_hard_loss, float grad_scale, float* out_losses,
+                                         int64_t n_rows, int64_t n_tea_rows, int vocab, int dtype,
+                                         unsigned round_flags) {
+    if (!s) return LICV_ERR_NULL_POINTER;
+    if (n_rows < 0 || n_tea_rows < 0 || vocab <= 0) return LICV_ERR_BAD_ARGUMENT;
+    if (!out_losses) return LICV_ERR_NULL_POINTER;
+    if (n_rows > 0 && !stu) return LICV_ERR_NULL_POINTER;
+    auto* slot = acquire(s);
+    Carver c{slot->scratch, s->bytes};
+    const int64_t sb = n_rows * vocab * esize(dtype), tb = n_tea_rows * vocab * esize(dtype);
+    // device rows are padded to a multiple of 8 elements so that every row starts 16-byte aligned
+    void* d_stu = c.take(sb > 0 ? sb : 16);
+    void* d_tea = (tea && tb > 0) ? c.take(tb) : nullptr;
+    int32_t* d_ktr = kl_tea_row ? static_cast<int32_t*>(c.take(n_rows * 4 + 4)) : nullptr;
+    int64_t* d_lab = ce_label ? static_cast<int64_t*>(c.take(n_rows * 8 + 8)) : nullptr;
+    float* d_loss = static_cast<float*>(c.take(16));
+    const int64_t wsb = licv_kd_loss_workspace_bytes(n_rows);
+    void* d_ws = c.take(wsb);
+    if (!c.ok) return LICV_ERR_WORKSPACE;
+    cudaStream_t st = slot->stream;
+    LICV_CUDA(cudaMemsetAsync(d_ws, 0, 16, st));
+    if (sb > 0) LICV_CUDA(cudaMemcpyAsync(d_stu, stu, (size_t)sb, cudaMemcpyHostToDevice, st));
+    if (d_tea) LICV_CUDA(cudaMemcpyAsync(d_tea, tea, (size_t)tb, cudaMemcpyHostToDevice, st));
+    if (d_ktr) LICV_CUDA(cudaMemcpyAsync(d_ktr, kl_tea_row, (size_t)n_rows * 4, cudaMemcpyHostToDevice, st));
+    if (d_lab) LICV_CUDA(cudaMemcpyAsync(d_lab, ce_label, (size_t)n_rows * 8, cudaMemcpyHostToDevice, st));
+    if (int rc = licv_kd_loss_fwd_bwd(d_stu, dstu ? d_stu : nullptr, d_tea, d_ktr, d_lab, nullptr,
+                                      n_kl, n_ce, temperature, kl_eps, hard_loss_weight,
+                                      only_hard_loss, grad_scale, d_loss, d_ws, n_rows, vocab, vocab,
+                                      vocab, dtype, round_flags,
+                                      reinterpret_cast<licv_stream_t>(st)))
+        return rc;
+    if (dstu && sb > 0) LICV_CUDA(cudaMemcpyAsync(dstu, d_stu, (size_t)sb, cudaMemcpyDeviceToHost, st));
+    LICV_CUDA(cudaMemcpyAsync(out_losses, d_loss, 12, cudaMemcpyDeviceToHost, st));
+    return LICV_OK;
+}

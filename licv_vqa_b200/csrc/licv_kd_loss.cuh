@@ -1,0 +1,29 @@
+// Argument block shared by the distillation-loss kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace licv {
+
+struct KdArgs {
+    const void* stu;
+    void* dstu;              // may alias stu; nullptr = loss only
+    const void* tea;
+    const int32_t* kl_tea_row;  // nullptr = identity pairing
+    const int64_t* ce_label;    // nullptr = no CE term
+    const int32_t* counts;      // device {N, M} or nullptr
+    int64_t n_kl, n_ce;         // host N, M (used when counts == nullptr)
+    float temperature, kl_eps, hard_loss_weight, grad_scale;
+    bool only_hard_loss;
+    float* out_losses;          // {kl, ce, total}
+    unsigned* counter;          // zero on entry, zero on exit
+    float* row_loss;            // [2 * n_rows]: per-row KL sums, per-row CE values
+    int64_t n_rows;
+    int vocab;
+    int64_t stu_stride, tea_stride;  // elements
+    unsigned round_flags;
+};
+
+int launch_kd_generic(const KdArgs& a, int dtype, cudaStream_t st);
+
+}  // namespace licv

@@ -1,0 +1,377 @@
+// Small kernels and host plumbing around the two hot kernels: device query, the encoder product
+// (a1+a2) and its backward, get_mask (a6), row pairing / label preparation (a6+a7+a9), and the
+// fused clip + AdamW step on the flat ICV parameter buffer (f2).
+#include <mutex>
+
+#include "licv_common.cuh"
+
+namespace licv {
+
+const DeviceInfo& device_info() {
+    // one entry per device ordinal; a process here drives one GPU, so a small fixed table will do
+    static DeviceInfo table[64];
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        static DeviceInfo bad;
+        cudaGetLastError();
+        return bad;
+    }
+    DeviceInfo& info = table[dev];
+    if (info.sm_count == 0) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (info.sm_count == 0) {
+            cudaDeviceProp prop;
+            if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
+                info.cc_major = prop.major;
+                info.cc_minor = prop.minor;
+                info.status = (prop.major == 10) ? LICV_OK : LICV_ERR_NO_DEVICE;
+                info.sm_count = prop.multiProcessorCount;
+            } else {
+                cudaGetLastError();
+                info.sm_count = -1;
+            }
+        }
+    }
+    return info;
+}
+
+namespace {
+
+__device__ __forceinline__ float sigmoidf(float a) { return 1.0f / (1.0f + __expf(-a)); }
+
+__global__ void icv_scale_kernel(const float* __restrict__ alpha, const float* __restrict__ vec,
+                                 float* __restrict__ icv, int n_layers, int d, int use_sigmoid) {
+    const int64_t n4 = (int64_t)n_layers * d / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int l = (int)(i * 4 / d);
+        float a = alpha[l];
+        if (use_sigmoid) a = sigmoidf(a);
+        float4 v = reinterpret_cast<const float4*>(vec)[i];
+        v.x *= a; v.y *= a; v.z *= a; v.w *= a;
+        reinterpret_cast<float4*>(icv)[i] = v;
+    }
+}
+
+// one CTA per layer: d_vec = alpha_eff * d_icv, d_alpha = (d_icv . vec) * dsigmoid
+__global__ void __launch_bounds__(256)
+icv_scale_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ vec,
+                     const float* __restrict__ d_icv, float* __restrict__ d_vec,
+                     float* __restrict__ d_alpha, int d, int use_sigmoid) {
+    __shared__ float slab[8];
+    const int l = blockIdx.x;
+    float a = alpha[l];
+    float da = 1.0f;
+    if (use_sigmoid) {
+        a = sigmoidf(a);
+        da = a * (1.0f - a);
+    }
+    const float4* g4 = reinterpret_cast<const float4*>(d_icv + (int64_t)l * d);
+    const float4* v4 = reinterpret_cast<const float4*>(vec + (int64_t)l * d);
+    float4* o4 = reinterpret_cast<float4*>(d_vec + (int64_t)l * d);
+    float dot = 0.f;
+    for (int i = threadIdx.x; i < d / 4; i += blockDim.x) {
+        const float4 g = g4[i];
+        const float4 v = v4[i];
+        dot = fmaf(g.x, v.x, dot); dot = fmaf(g.y, v.y, dot);
+        dot = fmaf(g.z, v.z, dot); dot = fmaf(g.w, v.w, dot);
+        o4[i] = make_float4(a * g.x, a * g.y, a * g.z, a * g.w);
+    }
+    if (d_alpha == nullptr) return;
+    dot = warp_sum(dot);
+    if ((threadIdx.x & 31) == 0) slab[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += slab[w];
+        d_alpha[l] = s * da;
+    }
+}
+
+__global__ void get_mask_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ len,
+                                int64_t pad, int batch, int seq, uint8_t* __restrict__ mask) {
+    const int n = batch * seq;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int b = i / seq, t = i - b * seq;
+        mask[i] = (uint8_t)(((int64_t)t >= len[b]) && (ids[i] != pad));
+    }
+}
+
+// exclusive rank of this thread's flag among the CTA's flags; `base` carries across tiles
+__device__ __forceinline__ int cta_rank(bool flag, int* warp_tot, int* tile_total) {
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = 0, tot = 0;
+    for (int w = 0; w < nw; ++w) {
+        const int c = warp_tot[w];
+        if (w < warp) off += c;
+        tot += c;
+    }
+    *tile_total = tot;
+    return off + __popc(bal & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(1024)
+kd_prepare_rows_kernel(const int64_t* __restrict__ s_ids, const int64_t* __restrict__ s_len,
+                       const int64_t* __restrict__ s_att, const int64_t* __restrict__ t_ids,
+                       const int64_t* __restrict__ t_len, int64_t pad, int64_t image_tok,
+                       int ce_variant, int batch, int Tq, int Tt, int32_t* __restrict__ kl_tea_row,
+                       int64_t* __restrict__ ce_label, int32_t* __restrict__ counts) {
+    extern __shared__ int32_t stu_by_rank[];  // [batch*Tq]: flat student row of the k-th KL row
+    __shared__ int warp_tot[32];
+    __shared__ int s_m;
+    const int ns = batch * Tq, nt = batch * Tt;
+    if (threadIdx.x == 0) s_m = 0;
+
+    // student rows in row-major order -> rank
+    int base = 0;
+    for (int i0 = 0; i0 < ns; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        bool sel = false;
+        if (i < ns) {
+            const int b = i / Tq, t = i - b * Tq;
+            sel = ((int64_t)t >= s_len[b]) && (s_ids[i] != pad);
+            kl_tea_row[i] = -1;
+        }
+        int tot;
+        const int rk = cta_rank(sel, warp_tot, &tot);
+        if (sel) stu_by_rank[base + rk] = i;
+        base += tot;
+    }
+    const int n_stu = base;
+    __syncthreads();
+
+    // teacher rows in row-major order: the k-th one pairs with the k-th student row
+    base = 0;
+    for (int i0 = 0; i0 < nt; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        bool sel = false;
+        if (i < nt) {
+            const int b = i / Tt, t = i - b * Tt;
+            sel = ((int64_t)t >= t_len[b]) && (t_ids[i] != pad);
+        }
+        int tot;
+        const int rk = cta_rank(sel, warp_tot, &tot);
+        if (sel && base + rk < n_stu) kl_tea_row[stu_by_rank[base + rk]] = i;
+        base += tot;
+    }
+    const int n_tea = base;
+
+    // next-token labels for labels = input_ids
+    int m_local = 0;
+    if (ce_label != nullptr) {
+        for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+            const int b = i / Tq, t = i - b * Tq;
+            int64_t lab = -100;
+            if (t + 1 < Tq) {
+                lab = s_ids[i + 1];
+                if (ce_variant != 2) {
+                    if (s_att != nullptr && s_att[i + 1] == 0) lab = -100;
+                    if (ce_variant == 1 && lab == image_tok) lab = -100;
+                }
+            }
+            ce_label[i] = lab;
+            m_local += (lab != -100);
+        }
+        m_local = (int)warp_sum((float)m_local);  // exact: counts stay far below 2^24
+        if ((threadIdx.x & 31) == 0 && m_local) atomicAdd(&s_m, m_local);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        counts[0] = n_stu;
+        counts[1] = s_m;
+        counts[2] = n_tea;
+        counts[3] = 0;
+    }
+}
+
+// ---- optimizer ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ g, int64_t n, float prescale, float* __restrict__ acc) {
+    __shared__ float slab[8];
+    float s = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = g[i] * prescale;
+        s = fmaf(x, x, s);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) slab[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += slab[w];
+        atomicAdd(acc, t);
+    }
+}
+
+struct AdamArgs {
+    float* p; const float* g; float* m; float* v;
+    int64_t n_vec, n_alpha;
+    float lr_vec, lr_alpha, beta1, beta2, eps, wd, prescale, max_norm;
+    float bc1, bc2_sqrt;   // 1 - beta1^t, sqrt(1 - beta2^t)
+    float* norm_out;
+    float* acc;            // workspace[0]: sum of squares
+    unsigned* ticket;      // workspace[1]
+};
+
+__global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
+    // every CTA reads the norm before taking a ticket; the last ticket holder clears the workspace
+    float coef = a.prescale;
+    const float norm = sqrtf(*reinterpret_cast<volatile float*>(a.acc));
+    if (a.max_norm > 0.f) {
+        const float c = a.max_norm / (norm + 1e-6f);   // torch.nn.utils.clip_grad_norm_
+        coef *= fminf(c, 1.0f);
+    }
+    const int64_t n = a.n_vec + a.n_alpha;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const float lr = i < a.n_vec ? a.lr_vec : a.lr_alpha;
+        const float g = a.g[i] * coef;
+        float p = a.p[i] * (1.0f - lr * a.wd);
+        const float m = a.beta1 * a.m[i] + (1.0f - a.beta1) * g;
+        const float v = a.beta2 * a.v[i] + (1.0f - a.beta2) * g * g;
+        const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+        p -= (lr / a.bc1) * (m / denom);
+        a.p[i] = p; a.m[i] = m; a.v[i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0 && a.norm_out) *a.norm_out = norm;
+        __threadfence();
+        if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) {
+            *a.acc = 0.f;
+            *a.ticket = 0u;
+        }
+    }
+}
+
+}  // namespace
+}  // namespace licv
+
+using namespace licv;
+
+extern "C" const char* licv_status_string(int status) {
+    switch (status) {
+        case LICV_OK: return "ok";
+        case LICV_ERR_NULL_POINTER: return "null pointer";
+        case LICV_ERR_BAD_DTYPE: return "unsupported dtype (bf16, fp16, fp32 only)";
+        case LICV_ERR_BAD_DIM:
+            return "unsupported hidden size (rows must be whole 16-byte vectors, at most 32 KB)";
+        case LICV_ERR_MISALIGNED: return "pointer not 16-byte aligned";
+        case LICV_ERR_BAD_ARGUMENT: return "bad argument";
+        case LICV_ERR_WORKSPACE: return "workspace too small";
+        case LICV_ERR_NO_DEVICE: return "no sm_100 (B200) device: liblicv_b200 has no other path";
+        default: break;
+    }
+    if (status > 0) return cudaGetErrorString(static_cast<cudaError_t>(status));
+    return "unknown status";
+}
+
+extern "C" int licv_abi_version(void) { return LICV_ABI_VERSION; }
+
+extern "C" int licv_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    const DeviceInfo& d = device_info();
+    if (sm_count) *sm_count = d.sm_count;
+    if (cc_major) *cc_major = d.cc_major;
+    if (cc_minor) *cc_minor = d.cc_minor;
+    return d.status;
+}
+
+extern "C" int licv_icv_scale(const float* alpha_raw, const float* vec, float* icv, int n_layers,
+                              int d, int use_sigmoid, licv_stream_t stream) {
+    if (device_info().status != LICV_OK) return device_info().status;
+    if (n_layers < 0 || d <= 0 || d % 4 != 0) return LICV_ERR_BAD_DIM;
+    if (n_layers == 0) return LICV_OK;
+    if (!alpha_raw || !vec || !icv) return LICV_ERR_NULL_POINTER;
+    if (!aligned16(vec) || !aligned16(icv)) return LICV_ERR_MISALIGNED;
+    const int64_t n4 = (int64_t)n_layers * d / 4;
+    const int grid = (int)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184);
+    icv_scale_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        alpha_raw, vec, icv, n_layers, d, use_sigmoid);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int licv_icv_scale_bwd(const float* alpha_raw, const float* vec, const float* d_icv,
+                                  float* d_vec, float* d_alpha_raw, int n_layers, int d,
+                                  int use_sigmoid, licv_stream_t stream) {
+    if (device_info().status != LICV_OK) return device_info().status;
+    if (n_layers < 0 || d <= 0 || d % 4 != 0) return LICV_ERR_BAD_DIM;
+    if (n_layers == 0) return LICV_OK;
+    if (!alpha_raw || !vec || !d_icv || !d_vec) return LICV_ERR_NULL_POINTER;
+    if (!aligned16(vec) || !aligned16(d_icv) || !aligned16(d_vec)) return LICV_ERR_MISALIGNED;
+    icv_scale_bwd_kernel<<<n_layers, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        alpha_raw, vec, d_icv, d_vec, d_alpha_raw, d, use_sigmoid);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int licv_get_mask(const int64_t* input_ids, const int64_t* mask_length,
+                             int64_t pad_token_id, int batch, int seq_len, uint8_t* mask,
+                             licv_stream_t stream) {
+    if (device_info().status != LICV_OK) return device_info().status;
+    if (batch < 0 || seq_len < 0) return LICV_ERR_BAD_ARGUMENT;
+    if (batch == 0 || seq_len == 0) return LICV_OK;
+    if (!input_ids || !mask_length || !mask) return LICV_ERR_NULL_POINTER;
+    const int n = batch * seq_len;
+    const int grid = (n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184;
+    get_mask_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        input_ids, mask_length, pad_token_id, batch, seq_len, mask);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int licv_kd_prepare_rows(const int64_t* stu_ids, const int64_t* stu_mask_length,
+                                    const int64_t* stu_attention_mask, const int64_t* tea_ids,
+                                    const int64_t* tea_mask_length, int64_t pad_token_id,
+                                    int64_t image_token_id, int ce_variant, int batch, int stu_len,
+                                    int tea_len, int32_t* kl_tea_row, int64_t* ce_label,
+                                    int32_t* counts, licv_stream_t stream) {
+    if (device_info().status != LICV_OK) return device_info().status;
+    if (batch <= 0 || stu_len <= 0 || tea_len <= 0 || ce_variant < 0 || ce_variant > 2)
+        return LICV_ERR_BAD_ARGUMENT;
+    if (!stu_ids || !stu_mask_length || !tea_ids || !tea_mask_length || !kl_tea_row || !counts)
+        return LICV_ERR_NULL_POINTER;
+    const size_t smem = (size_t)batch * stu_len * sizeof(int32_t);
+    if (smem > 200 * 1024) return LICV_ERR_BAD_ARGUMENT;  // > 51200 student positions
+    if (smem > 48 * 1024) {
+        static std::once_flag once;
+        std::call_once(once, [] {
+            cudaFuncSetAttribute(kd_prepare_rows_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        });
+    }
+    kd_prepare_rows_kernel<<<1, 1024, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+        stu_ids, stu_mask_length, stu_attention_mask, tea_ids, tea_mask_length, pad_token_id,
+        image_token_id, ce_variant, batch, stu_len, tea_len, kl_tea_row, ce_label, counts);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int licv_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                               int64_t n_vec, int64_t n_alpha, float lr_vec, float lr_alpha,
+                               float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                               float grad_prescale, float max_grad_norm, float* norm_out,
+                               void* workspace, licv_stream_t stream) {
+    if (device_info().status != LICV_OK) return device_info().status;
+    if (n_vec < 0 || n_alpha < 0 || step < 1) return LICV_ERR_BAD_ARGUMENT;
+    const int64_t n = n_vec + n_alpha;
+    if (n == 0) return LICV_OK;
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !workspace) return LICV_ERR_NULL_POINTER;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    AdamArgs a;
+    a.p = param; a.g = grad; a.m = exp_avg; a.v = exp_avg_sq;
+    a.n_vec = n_vec; a.n_alpha = n_alpha;
+    a.lr_vec = lr_vec; a.lr_alpha = lr_alpha; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+    a.wd = weight_decay; a.prescale = grad_prescale; a.max_norm = max_grad_norm;
+    a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    a.norm_out = norm_out;
+    a.acc = static_cast<float*>(workspace);
+    a.ticket = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + 4);
+    const int grid = (int)((n + 1023) / 1024 < 148 ? (n + 1023) / 1024 : 148);
+    sumsq_kernel<<<grid, 256, 0, st>>>(grad, n, grad_prescale, a.acc);
+    adamw_kernel<<<grid, 256, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,174 @@
+"""Frozen-LMM wrapper that injects the in-context vectors into the residual stream.
+
+Drop-in for the reference's LearnableICVInterventionLMM (icv_src/icv_model/icv_intervention.py:
+10-129): same constructor, `forward(icv=None, *args, **kwargs)`, `generate(icv=None, ...)`,
+`toggle_intervention`, `intervention_status` (setter raises ValueError on a non-bool),
+`intervention_enabled`, `intervention_layers`, `intervention_layer_names`, `layer_to_icv_index`,
+`device`, `lmm`.  `icv` is the pre-multiplied [1, n_hooked_layers, d] tensor.
+
+What is different underneath:
+
+* the baukit ``TraceDict`` (rebuilt - named-module scan, 32 hook registrations, a regex per layer
+  call - on every forward/generate, icv_intervention.py:88-98) is replaced by torch forward hooks
+  installed ONCE; a call only swaps the active ICV state in and out;
+* the hook body (icv_intervention.py:61-86, five eager kernels + autograd's ~10 in backward + the
+  retained clones) is one fused sm_100a kernel each way (`ops.inject`), saving only `h`;
+* the per-layer d_shift vectors are accumulated by the backward kernels straight into one
+  [L, d] fp32 buffer that becomes `icv.grad`'s source - no per-layer zero-padded index_put;
+* hooks stay armed with the call's ICV after `forward` returns, so activation-checkpoint
+  recomputation during backward re-injects (the reference's context manager has already removed
+  its hooks by then, icv_intervention.py:112-113).
+"""
+from __future__ import annotations
+
+import re
+from typing import List, Optional, Union
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+class _ActiveICV:
+    """The ICV of one forward/generate call, fanned out per hooked layer."""
+
+    __slots__ = ("icv", "shifts", "sink", "icv_dtype")
+
+    def __init__(self, icv: torch.Tensor):
+        if icv.dim() != 3 or icv.shape[0] != 1:
+            raise ValueError(f"icv must be [1, n_layers, hidden], got {tuple(icv.shape)}")
+        self.icv = icv
+        self.icv_dtype = icv.dtype
+        # the kernels take the shift as fp32 (exact for bf16/fp16 ICVs); where the reference's
+        # arithmetic would round because the ICV itself is low precision is carried by round_flags
+        icv32 = icv if icv.dtype == torch.float32 else icv.float()
+        self.shifts, self.sink = ops.fan_out_shifts(icv32.contiguous())
+
+
+class LearnableICVInterventionLMM(nn.Module):
+    def __init__(
+        self,
+        lmm: nn.Module,
+        enable_intervention=True,
+        intervention_layer: Union[int, List[int]] = None,
+        layer_format: str = None,
+        total_layers: int = None,
+        residual_dtype: str = "promote",
+    ):
+        """``residual_dtype``: "promote" (default) returns what the reference returns - torch type
+        promotion of (hidden, icv), i.e. fp32 for an fp32 ICV on bf16/fp16 hidden states;
+        "keep" rounds the result back to the hidden states' dtype (2 bytes/element out)."""
+        super().__init__()
+        self.lmm = lmm
+        if residual_dtype not in ("promote", "keep"):
+            raise ValueError("residual_dtype must be 'promote' or 'keep'")
+        self.residual_dtype = residual_dtype
+        self._active: Optional[_ActiveICV] = None
+        self._hook_handles = []
+
+        if enable_intervention:
+            self.total_layers = total_layers
+            self.intervention_layers = self._prepare_layers(intervention_layer)
+            self.intervention_layer_names = [
+                layer_format.replace("<LAYER_NUM>", str(layer))
+                for layer in self.intervention_layers
+            ]
+            self.layer_to_icv_index = {
+                int(layer_id): int(icv_idx)
+                for icv_idx, layer_id in enumerate(self.intervention_layers)
+            }
+            self.intervention_enabled = True
+            self._install_hooks()
+
+    def _prepare_layers(self, layers):
+        if layers == -1:
+            return list(range(self.total_layers))
+        return [layers] if isinstance(layers, int) else layers
+
+    # ------------------------------------------------------------------ hooks (installed once)
+    def _install_hooks(self):
+        named = dict(self.lmm.named_modules())
+        for name in self.intervention_layer_names:
+            if name not in named:
+                raise LookupError(name)  # what baukit raises for an unknown layer name
+            # the reference keys the ICV row by the FIRST number in the module name
+            # (icv_intervention.py:63), KeyError included when that is not a hooked layer id
+            layer_idx = int(re.findall(r"\d+", name)[0])
+            icv_index = self.layer_to_icv_index[layer_idx]
+            self._hook_handles.append(
+                named[name].register_forward_hook(self._make_hook(icv_index)))
+
+    def _make_hook(self, icv_index: int):
+        def hook(_module, _inputs, output):
+            active = self._active
+            if active is None:
+                return None
+            if isinstance(output, tuple):
+                hidden_states, *rest = output
+                return (self._inject(hidden_states, active, icv_index),) + tuple(rest)
+            if isinstance(output, torch.Tensor):
+                return self._inject(output, active, icv_index)
+            return None
+
+        return hook
+
+    def _inject(self, hidden_states, active: _ActiveICV, icv_index: int):
+        flags, ref_dtype = ops.reference_rounding(hidden_states.dtype, active.icv_dtype)
+        out_dtype = ref_dtype if self.residual_dtype == "promote" else hidden_states.dtype
+        return ops.inject(hidden_states, active.shifts[icv_index], out_dtype, flags,
+                          active.sink[icv_index])
+
+    def remove_hooks(self):
+        for h in self._hook_handles:
+            h.remove()
+        self._hook_handles = []
+
+    # ------------------------------------------------------------------ reference API
+    @property
+    def device(self):
+        return self.lmm.device
+
+    @property
+    def intervention_status(self) -> bool:
+        return self.intervention_enabled
+
+    @intervention_status.setter
+    def intervention_status(self, value: bool):
+        if not isinstance(value, bool):
+            raise ValueError("Intervention status must be a boolean value.")
+        self.intervention_enabled = value
+
+    def toggle_intervention(self, enable: bool):
+        self.intervention_status = enable
+
+    def _run(self, fn, icv, args, kwargs):
+        enabled = getattr(self, "intervention_enabled", False)
+        previous = self._active
+        if enabled:
+            if icv is None:
+                # the reference fails inside its hook with `None[:, idx]`
+                raise TypeError("'NoneType' object is not subscriptable: intervention is enabled "
+                                "but no icv was given")
+            self._active = _ActiveICV(icv)
+            # stays armed after the call for checkpoint recomputation during backward
+            return fn(*args, **kwargs)
+        self._active = None
+        try:
+            return fn(*args, **kwargs)
+        finally:
+            # a hook-less call (the teacher pass, icv_module.py:103-105) must not disarm the
+            # student's state that backward-time recomputation may still need
+            self._active = previous
+
+    def forward(self, icv=None, *args, **kwargs):
+        """lmm(*args, **kwargs) with the ICV injected at every hooked layer (if enabled)."""
+        return self._run(self.lmm, icv, args, kwargs)
+
+    def generate(self, icv=None, *args, **kwargs):
+        """lmm.generate(*args, **kwargs) with the ICV injected at every hooked layer (if enabled)."""
+        return self._run(self.lmm.generate, icv, args, kwargs)
+
+    def release(self):
+        """Drop the armed ICV state (frees the saved graph references)."""
+        self._active = None

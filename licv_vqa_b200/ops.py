@@ -1,0 +1,380 @@
+"""Custom autograd ops over the C ABI (liblicv_b200.so): the injection and the distillation loss.
+
+Each op launches hand-written sm_100a kernels on torch's current stream with raw device pointers
+(PyTorch owns every buffer; it is plumbing, not the product).  CUDA tensors only: there is no CPU
+path, no Triton, no multi-backend dispatch - a CPU tensor is a hard error.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _abi
+
+_DT = {torch.float32: _abi.F32, torch.bfloat16: _abi.BF16, torch.float16: _abi.F16}
+_LOWP = (torch.bfloat16, torch.float16)
+IGNORE_INDEX = -100
+
+
+def _code(dtype: torch.dtype) -> int:
+    try:
+        return _DT[dtype]
+    except KeyError:
+        raise TypeError(f"licv_vqa_b200 supports float32 / bfloat16 / float16, got {dtype}") from None
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "licv_vqa_b200 runs on B200 GPUs only (no CPU path, no fallback): got a "
+                f"{t.device.type} tensor")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+# ---------------------------------------------------------------------------------------------
+# where the reference's eager chain rounds (see include/licv_b200.h LICV_ROUND_*)
+# ---------------------------------------------------------------------------------------------
+def reference_rounding(h_dtype: torch.dtype, icv_dtype: torch.dtype, autocast: bool | None = None):
+    """(round_flags, result dtype) the reference's ``intervention_function``
+    (icv_intervention.py:66-72) produces for hidden states of ``h_dtype`` and an ``icv`` tensor of
+    ``icv_dtype`` under torch type promotion, with CUDA autocast on or off (``norm`` runs in fp32
+    under autocast; ``+ * /`` follow their operands)."""
+    if h_dtype not in _LOWP:
+        return 0, torch.float32
+    if autocast is None:
+        autocast = torch.is_autocast_enabled("cuda")
+    ry = icv_dtype == h_dtype
+    rnh = not autocast
+    rny = ry and not autocast
+    rt = ry and rny
+    flags = ((_abi.ROUND_Y if ry else 0) | (_abi.ROUND_NH if rnh else 0)
+             | (_abi.ROUND_NY if rny else 0) | (_abi.ROUND_T if rt else 0))
+    return flags, (h_dtype if (rt and rnh) else torch.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# a1 + a2: icv = get_alpha().unsqueeze(-1) * in_context_vector
+# ---------------------------------------------------------------------------------------------
+class _ICVScale(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, alpha_raw, vec, use_sigmoid):
+        _need_cuda(alpha_raw, vec)
+        if alpha_raw.dtype != torch.float32 or vec.dtype != torch.float32:
+            raise TypeError("icv_scale: the ICV parameters are fp32")
+        _, L, d = vec.shape
+        a = alpha_raw.contiguous()
+        v = vec.contiguous()
+        icv = torch.empty_like(v)
+        _abi.check(_abi.load().licv_icv_scale(a.data_ptr(), v.data_ptr(), icv.data_ptr(), L, d,
+                                              int(use_sigmoid), _stream()), "licv_icv_scale")
+        ctx.save_for_backward(a, v)
+        ctx.use_sigmoid = bool(use_sigmoid)
+        return icv
+
+    @staticmethod
+    def backward(ctx, d_icv):
+        a, v = ctx.saved_tensors
+        _, L, d = v.shape
+        g = d_icv.contiguous().float()
+        d_vec = torch.empty_like(v)
+        d_alpha = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        _abi.check(_abi.load().licv_icv_scale_bwd(a.data_ptr(), v.data_ptr(), g.data_ptr(),
+                                                  d_vec.data_ptr(), _ptr(d_alpha), L, d,
+                                                  int(ctx.use_sigmoid), _stream()),
+                   "licv_icv_scale_bwd")
+        return d_alpha, (d_vec if ctx.needs_input_grad[1] else None), None
+
+
+def icv_scale(alpha_raw: torch.Tensor, vec: torch.Tensor, use_sigmoid: bool) -> torch.Tensor:
+    """``sigmoid?(alpha)[..., None] * vec``: alpha_raw [1,L], vec [1,L,d] -> icv [1,L,d] (fp32).
+
+    One kernel each way instead of sigmoid + unsqueeze + mul and their autograd
+    (global_icv_encoder.py:40-43, icv_module.py:89-92, inference.py:311)."""
+    return _ICVScale.apply(alpha_raw, vec, use_sigmoid)
+
+
+# ---------------------------------------------------------------------------------------------
+# a3 + a4: residual-stream injection
+# ---------------------------------------------------------------------------------------------
+def inject_forward(h: torch.Tensor, shift: torch.Tensor, out_dtype: torch.dtype | None = None,
+                   round_flags: int = 0) -> torch.Tensor:
+    """out = (h + shift)/||h + shift|| * ||h|| per token (no autograd).  h [..., d], shift [d] fp32."""
+    _need_cuda(h, shift)
+    d = h.shape[-1]
+    if shift.dtype != torch.float32 or shift.numel() != d:
+        raise ValueError("shift must be an fp32 vector of the hidden size")
+    hc = h.contiguous()
+    sc = shift.contiguous()
+    out_dtype = out_dtype or h.dtype
+    out = torch.empty(hc.shape, dtype=out_dtype, device=h.device)
+    n_tok = hc.numel() // d if d else 0
+    _abi.check(_abi.load().licv_inject_fwd(hc.data_ptr(), sc.data_ptr(), out.data_ptr(), n_tok, d,
+                                           _code(h.dtype), _code(out_dtype), round_flags,
+                                           _stream()), "licv_inject_fwd")
+    return out
+
+
+def inject_backward(h, g, shift, d_shift, want_dh=True, round_flags=0):
+    """dh (or None) for g = dL/dout; accumulates sum_tokens g_y into the fp32 vector d_shift."""
+    _need_cuda(h, g, shift, d_shift)
+    d = h.shape[-1]
+    hc = h.contiguous()
+    gc = g.contiguous()
+    dh = torch.empty_like(hc) if want_dh else None
+    n_tok = hc.numel() // d if d else 0
+    _abi.check(_abi.load().licv_inject_bwd(hc.data_ptr(), gc.data_ptr(), shift.data_ptr(),
+                                           _ptr(dh), d_shift.data_ptr(), n_tok, d, _code(h.dtype),
+                                           _code(g.dtype), round_flags, _stream()),
+               "licv_inject_bwd")
+    return dh
+
+
+class _Inject(torch.autograd.Function):
+    """h, shift -> out.  Saves h only (the reference's autograd keeps several fp32 [B,T,d]
+    intermediates per layer plus baukit's clone)."""
+
+    @staticmethod
+    def forward(ctx, h, shift, out_dtype, round_flags, sink_row):
+        out = inject_forward(h, shift, out_dtype, round_flags)
+        ctx.save_for_backward(h, shift)
+        ctx.round_flags = round_flags
+        ctx.sink_row = sink_row
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, shift = ctx.saved_tensors
+        row = ctx.sink_row
+        if row is None:
+            row = torch.zeros_like(shift)
+        else:
+            ctx.sink_row = None  # a second backward through this node must not double-count
+        dh = inject_backward(h, g, shift.contiguous(), row, ctx.needs_input_grad[0],
+                             ctx.round_flags)
+        return dh, (row if ctx.needs_input_grad[1] else None), None, None, None
+
+
+def inject(h, shift, out_dtype=None, round_flags=0, sink_row=None):
+    """Differentiable injection.  ``sink_row``: optional zero-initialised fp32 [d] buffer that
+    receives d_shift (lets a whole model's per-layer gradients land in one [L,d] buffer)."""
+    if not (torch.is_grad_enabled() and (h.requires_grad or shift.requires_grad)):
+        return inject_forward(h, shift, out_dtype, round_flags)
+    return _Inject.apply(h, shift, out_dtype, round_flags, sink_row)
+
+
+class _ShiftFanout(torch.autograd.Function):
+    """icv [1,L,d] -> L per-layer shift vectors.  Backward hands back the shared [L,d] sink the
+    per-layer injection backwards accumulated into - no stack/cat, no per-layer zero padding."""
+
+    @staticmethod
+    def forward(ctx, icv32, sink):
+        ctx.sink = sink
+        ctx.shape = icv32.shape
+        flat = icv32.reshape(icv32.shape[-2], icv32.shape[-1])
+        return tuple(flat[l] for l in range(flat.shape[0]))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        sink = ctx.sink
+        # zero-copy only for a full backward in which every layer's gradient IS its sink row; a
+        # partial call (reentrant checkpointing runs one nested backward per layer) is summed
+        # by autograd from per-call tensors instead
+        direct = all(g is not None and g.data_ptr() == sink[l].data_ptr() and g.dtype == sink.dtype
+                     for l, g in enumerate(grads))
+        if direct:
+            return sink.view(ctx.shape), None
+        rows = [torch.zeros_like(sink[l]) if g is None else g.to(sink.dtype)
+                for l, g in enumerate(grads)]
+        return torch.stack(rows).view(ctx.shape), None
+
+
+def fan_out_shifts(icv32: torch.Tensor):
+    """-> (tuple of L shift vectors [d], sink [L,d] fp32 zeros)."""
+    L, d = icv32.shape[-2], icv32.shape[-1]
+    sink = torch.zeros(L, d, dtype=torch.float32, device=icv32.device)
+    if torch.is_grad_enabled() and icv32.requires_grad:
+        return _ShiftFanout.apply(icv32, sink), sink
+    flat = icv32.reshape(L, d)
+    return tuple(flat[l] for l in range(L)), sink
+
+
+# ---------------------------------------------------------------------------------------------
+# a6: get_mask;  a6 + a7 + a9 label prep: row selection
+# ---------------------------------------------------------------------------------------------
+def get_mask(input_ids: torch.Tensor, mask_length: torch.Tensor, pad_token_id: int) -> torch.Tensor:
+    """mask[b,t] = (t >= mask_length[b]) & (input_ids[b,t] != pad)  (icv_module.py:136-148)."""
+    _need_cuda(input_ids, mask_length)
+    B, T = input_ids.shape
+    ids = input_ids.contiguous().long()
+    ml = mask_length.contiguous().long()
+    mask = torch.empty(B, T, dtype=torch.bool, device=ids.device)
+    _abi.check(_abi.load().licv_get_mask(ids.data_ptr(), ml.data_ptr(), int(pad_token_id), B, T,
+                                         mask.data_ptr(), _stream()), "licv_get_mask")
+    return mask
+
+
+CE_VARIANTS = {"idefics": 0, "idefics2": 1, "causal_lm": 2}
+
+
+def kd_prepare_rows(stu_ids, stu_mask_length, tea_ids, tea_mask_length, pad_token_id,
+                    stu_attention_mask=None, ce_variant="idefics", image_token_id=-1,
+                    want_ce=True):
+    """Row pairing and next-token labels without gathers or host syncs.
+
+    -> (kl_tea_row int32 [B*Tq], ce_label int64 [B*Tq] or None, counts int32 [4] = N, M, N_tea, 0)
+    """
+    _need_cuda(stu_ids, stu_mask_length, tea_ids, tea_mask_length, stu_attention_mask)
+    B, Tq = stu_ids.shape
+    Bt, Tt = tea_ids.shape
+    if B != Bt:
+        raise ValueError("student and teacher batches differ")
+    dev = stu_ids.device
+    s_ids = stu_ids.contiguous().long()
+    t_ids = tea_ids.contiguous().long()
+    s_len = stu_mask_length.contiguous().long()
+    t_len = tea_mask_length.contiguous().long()
+    s_att = None if stu_attention_mask is None else stu_attention_mask.contiguous().long()
+    kl_tea_row = torch.empty(B * Tq, dtype=torch.int32, device=dev)
+    ce_label = torch.empty(B * Tq, dtype=torch.int64, device=dev) if want_ce else None
+    counts = torch.empty(4, dtype=torch.int32, device=dev)
+    _abi.check(_abi.load().licv_kd_prepare_rows(
+        s_ids.data_ptr(), s_len.data_ptr(), _ptr(s_att), t_ids.data_ptr(), t_len.data_ptr(),
+        int(pad_token_id), int(image_token_id), CE_VARIANTS[ce_variant], B, Tq, Tt,
+        kl_tea_row.data_ptr(), _ptr(ce_label), counts.data_ptr(), _stream()),
+        "licv_kd_prepare_rows")
+    return kl_tea_row, ce_label, counts
+
+
+# ---------------------------------------------------------------------------------------------
+# a7 + a8 + a9 + a10: distillation loss
+# ---------------------------------------------------------------------------------------------
+_WS_CACHE: dict = {}
+
+
+def _workspace(device, n_rows):
+    """Per-(device, stream) workspace, grown on demand; its 16-byte header stays zero between
+    calls (the kernel restores it)."""
+    key = (device.index, _stream())
+    need = _abi.load().licv_kd_loss_workspace_bytes(int(n_rows))
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 4096), dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = ws
+    return ws
+
+
+def kd_loss_raw(stu, tea, kl_tea_row=None, ce_label=None, counts=None, n_kl=0, n_ce=0,
+                temperature=1.0, kl_eps=1e-6, hard_loss_weight=0.0, only_hard_loss=False,
+                grad_scale=1.0, in_place=True, want_grad=True, round_flags=_abi.ROUND_TEMPERED):
+    """One launch: losses [3] = (kl, ce, total) and d total / d stu.
+
+    stu [R,V] (last dim contiguous, rows strided), tea [Rt,V].  With ``in_place`` the gradient
+    overwrites ``stu``'s storage (the student logits are dead after the loss; the reference
+    already mutates its gathered copies in place, icv_module.py:122-123)."""
+    _need_cuda(stu, tea, kl_tea_row, ce_label, counts)
+    if stu.dim() != 2 or stu.stride(1) != 1:
+        raise ValueError("stu must be [R,V] with a contiguous last dimension")
+    R, V = stu.shape
+    if tea is not None:
+        if tea.dim() != 2 or tea.stride(1) != 1 or tea.shape[1] != V or tea.dtype != stu.dtype:
+            raise ValueError("tea must be [Rt,V] of the student's dtype with a contiguous last dim")
+    losses = torch.empty(3, dtype=torch.float32, device=stu.device)
+    dstu = None
+    if want_grad:
+        dstu = stu if in_place else torch.empty_strided(stu.shape, stu.stride(), dtype=stu.dtype,
+                                                        device=stu.device)
+    ws = _workspace(stu.device, R)
+    _abi.check(_abi.load().licv_kd_loss_fwd_bwd(
+        stu.data_ptr(), _ptr(dstu), _ptr(tea), _ptr(kl_tea_row), _ptr(ce_label), _ptr(counts),
+        int(n_kl), int(n_ce), float(temperature), float(kl_eps), float(hard_loss_weight),
+        int(bool(only_hard_loss)), float(grad_scale), losses.data_ptr(), ws.data_ptr(), R, V,
+        stu.stride(0) if R > 0 else V, (tea.stride(0) if tea is not None and tea.shape[0] > 0 else V),
+        _code(stu.dtype), int(round_flags), _stream()), "licv_kd_loss_fwd_bwd")
+    return losses, dstu
+
+
+class _KDLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, stu, tea, kl_tea_row, ce_label, counts, n_kl, n_ce, temperature, kl_eps,
+                hard_loss_weight, only_hard_loss, in_place, round_flags):
+        need = stu.requires_grad
+        src = stu.detach()
+        losses, dstu = kd_loss_raw(src, tea, kl_tea_row, ce_label, counts, n_kl, n_ce, temperature,
+                                   kl_eps, hard_loss_weight, only_hard_loss, 1.0, in_place, need,
+                                   round_flags)
+        ctx.dstu = dstu
+        if in_place and need:
+            # stu's storage now holds the gradient: bump its version so autograd refuses, loudly,
+            # any other backward that saved the logits themselves
+            torch.autograd.graph.increment_version(stu)
+        kl, ce = losses[0].clone(), losses[1].clone()
+        ctx.mark_non_differentiable(kl, ce)
+        return losses[2].clone(), kl, ce
+
+    @staticmethod
+    def backward(ctx, g_total, _g_kl, _g_ce):
+        dstu = ctx.dstu
+        ctx.dstu = None
+        if dstu is None:
+            return (None,) * 13
+        # upstream gradient of the scalar loss: applied in place, and skipped on the device
+        # (no traffic, no host sync) when it is exactly 1
+        g = g_total.detach().to(torch.float32).contiguous()
+        if dstu.is_contiguous():
+            _abi.check(_abi.load().licv_scale_inplace(dstu.data_ptr(), dstu.numel(), g.data_ptr(),
+                                                      _code(dstu.dtype), _stream()),
+                       "licv_scale_inplace")
+        else:  # padded row stride: rare, plain torch
+            dstu.mul_(g.to(dstu.dtype))
+        return (dstu,) + (None,) * 12
+
+
+def kd_loss(stu, tea, kl_tea_row=None, ce_label=None, counts=None, n_kl=None, n_ce=None,
+            temperature=1.0, kl_eps=1e-6, hard_loss_weight=0.0, only_hard_loss=False,
+            in_place=True, round_flags=_abi.ROUND_TEMPERED):
+    """Differentiable fused loss -> (total, kl, ce) scalars (kl/ce detached, for logging).
+
+    ``stu`` [R,V] is every student row; ``kl_tea_row``/``ce_label`` say which rows take part
+    (None/None = the compact form ``calculate_kl_divergence`` takes: row r vs teacher row r, no
+    CE).  ``counts`` (device) or ``n_kl``/``n_ce`` (host ints) give the means' denominators.
+    With ``in_place`` (default) the gradient is written over ``stu``'s storage, so ``stu`` must
+    not be read after this call.
+    """
+    R = stu.shape[0]
+    if counts is None:
+        if n_kl is None:
+            n_kl = R if kl_tea_row is None else None
+        if n_ce is None:
+            n_ce = 0 if ce_label is None else None
+        if n_kl is None or n_ce is None:
+            raise ValueError("give `counts` (device) or both n_kl and n_ce (host) with row lists")
+    return _KDLoss.apply(stu, tea, kl_tea_row, ce_label, counts, n_kl or 0, n_ce or 0,
+                         float(temperature), float(kl_eps), float(hard_loss_weight),
+                         bool(only_hard_loss), bool(in_place), int(round_flags))
+
+
+# ---------------------------------------------------------------------------------------------
+# f2: fused clip + AdamW on the flat ICV buffer
+# ---------------------------------------------------------------------------------------------
+def adamw_step(param, grad, exp_avg, exp_avg_sq, n_vec, n_alpha, lr_vec, lr_alpha, step,
+               beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-3, grad_prescale=1.0,
+               max_grad_norm=1.0, norm_out=None, workspace=None):
+    _need_cuda(param, grad, exp_avg, exp_avg_sq)
+    if workspace is None:
+        workspace = _workspace(param.device, 0)
+        # the optimizer uses bytes [8,16) of the shared zeroed header
+        ws_ptr = workspace.data_ptr() + 8
+    else:
+        ws_ptr = workspace.data_ptr()
+    _abi.check(_abi.load().licv_adamw_step(
+        param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), int(n_vec),
+        int(n_alpha), float(lr_vec), float(lr_alpha), float(beta1), float(beta2), float(eps),
+        float(weight_decay), int(step), float(grad_prescale), float(max_grad_norm), _ptr(norm_out),
+        ws_ptr, _stream()), "licv_adamw_step")

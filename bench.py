@@ -1,0 +1,600 @@
+#!/usr/bin/env python
+"""bench.py - L-ICV hot path on B200: train samples/s, kernel roofline, CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One STEP = one pass of the hot path over one batch of BASELINE.json configs[1] (idefics-9B shape:
+32 hooked layers, d = 4096, V = 32002, bs = 8 per GPU, 32 student tokens per sample, fp16 under
+the README's DeepSpeed "16-mixed" recipe, 4 answer tokens per sample as KL rows, every shifted
+non-pad position a CE row, hard_loss_weight = 0.5), on synthetic tensors:
+
+    icv = sigmoid?(alpha) * v                                  licv_icv_scale
+    32 x  out_l = inject(h_l, icv_l)                           licv_inject_fwd
+    row pairing + labels, KL + 0.5 CE fwd+bwd on the logits     licv_kd_prepare_rows, licv_kd_loss_fwd_bwd
+    32 x  dh_l, d_icv_l += inject_bwd(h_l, g_l, icv_l)          licv_inject_bwd
+    d_v, d_alpha                                                licv_icv_scale_bwd
+    (N > 1) all-reduce of the flat ICV gradient (131 104 fp32)  NCCL
+    clip + AdamW on the flat ICV parameters                     licv_adamw_step
+
+The frozen tower's GEMMs that produce h_l, g_l and the logits are stock cuBLAS and out of scope
+(BASELINE.json north_star); they are replaced here by resident synthetic tensors, a distinct
+buffer per layer so one step streams ~290 MB (> 126 MB L2) through the kernels.
+
+`value`  : samples/s over all ranks, inputs resident in HBM, whole step replayed as a CUDA graph.
+`e2e`    : the same step through the host-buffer C-ABI entry points (licv_*_host): every input
+           starts in pinned host memory and every result ends there.
+`roofline`: the dominant kernel of the step (licv_inject_bwd), CUDA-event timed per launch.
+`roofline_bw`: the same kernels at the bandwidth-bound shapes of configs[4] (inference sweep).
+`cpu_baseline`: oracle/torch_chain.py (the reference's eager op chain) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "train samples/s (L-ICV hot path: ICV inject fwd/bwd x32 layers + KL/CE fwd/bwd)"
+UNIT = "samples/s"
+
+CFG = dict(workload="configs[1]: idefics-9B shape, VQAv2 32-shot teacher vs zero-shot+ICV student",
+           layers=32, d=4096, vocab=32002, batch_per_gpu=8, student_tokens=32, kl_rows_per_sample=4,
+           teacher_rows=32, hard_loss_weight=0.5, temperature=1.0, kl_eps=1e-6, use_sigmoid=False,
+           alpha_init_value=0.1, dtype="fp16", recipe="DeepSpeed 16-mixed (fp16 ICV, no autocast)")
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic batch
+# ------------------------------------------------------------------------------------------------
+def make_batch(device, seed, dtype, pinned_host=False):
+    L, d, V = CFG["layers"], CFG["d"], CFG["vocab"]
+    B, T = CFG["batch_per_gpu"], CFG["student_tokens"]
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    dev = "cpu" if pinned_host else device
+
+    def mk(*shape, scale=1.0, dt=dtype):
+        t = (torch.randn(*shape, generator=g) * scale).to(dt)
+        if pinned_host:
+            return t.pin_memory()
+        return t.to(device)
+
+    batch = {}
+    batch["h"] = [mk(B * T, d, scale=float(1 + 29 * l / (L - 1))) for l in range(L)]
+    for h in batch["h"]:   # two "massive activation" channels, LLaMA-style
+        h[:, 7] *= 50
+        h[:, d // 3] *= -20
+    batch["g"] = [mk(B * T, d, scale=1e-2) for _ in range(L)]
+    stu = torch.randn(B * T, V, generator=g) * 3
+    tea = torch.randn(B * CFG["kl_rows_per_sample"], V, generator=g) * 3
+    # token ids: BOS, text, 4 answer tokens at the end of each sample; no padding in this batch
+    ids = torch.randint(3, V, (B, T), generator=g)
+    ids[:, 0] = 1
+    qx = torch.full((B,), T - CFG["kl_rows_per_sample"], dtype=torch.long)
+    # teacher sequence: only its answer rows are kept (the tower is out of scope): [B, 4]
+    t_ids = ids[:, T - CFG["kl_rows_per_sample"]:].clone()
+    t_len = torch.zeros(B, dtype=torch.long)
+    # +10 spike on the label in half of the KL rows
+    for b in range(B):
+        for k in range(CFG["kl_rows_per_sample"]):
+            r = b * T + (T - CFG["kl_rows_per_sample"]) + k
+            j = int(torch.randint(0, V, (1,), generator=g))
+            tea[b * CFG["kl_rows_per_sample"] + k, j] += 10
+            if k % 2:
+                stu[r, j] += 8
+    batch["stu"] = stu.to(dtype).pin_memory() if pinned_host else stu.to(dtype).to(device)
+    batch["tea"] = tea.to(dtype).pin_memory() if pinned_host else tea.to(dtype).to(device)
+    for k, v in (("ids", ids), ("qx", qx), ("t_ids", t_ids), ("t_len", t_len),
+                 ("att", torch.ones(B, T, dtype=torch.long))):
+        batch[k] = v.to(dev)
+    return batch
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region (NVML)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
+               0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+               0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the step, on resident tensors (C ABI launches on torch's current stream)
+# ------------------------------------------------------------------------------------------------
+class HotPath:
+    LAUNCHES_PER_STEP = 1 + 32 + 1 + 1 + 1 + 32 + 1 + 2   # + NCCL's own kernel when world > 1
+
+    def __init__(self, device, dtype, world):
+        from licv_vqa_b200 import _abi, ops
+        self.abi, self.ops, self.lib = _abi, ops, _abi.load()
+        self.device, self.dtype, self.world = device, dtype, world
+        self.code = {torch.float16: _abi.F16, torch.bfloat16: _abi.BF16,
+                     torch.float32: _abi.F32}[dtype]
+        L, d, V = CFG["layers"], CFG["d"], CFG["vocab"]
+        B, T = CFG["batch_per_gpu"], CFG["student_tokens"]
+        f32 = dict(dtype=torch.float32, device=device)
+        # flat parameter / gradient / moment buffers: [vec (L*d) | alpha (L)]
+        self.n_vec, self.n_alpha = L * d, L
+        self.param = torch.empty(L * d + L, **f32)
+        g = torch.Generator(device="cpu").manual_seed(426)
+        self.param[:L * d] = (torch.randn(L * d, generator=g) * 0.01).to(device)
+        self.param[L * d:] = CFG["alpha_init_value"]
+        self.grad = torch.zeros(L * d + L + 4, **f32)      # + logged scalars ride along
+        self.m = torch.zeros(L * d + L, **f32)
+        self.v = torch.zeros(L * d + L, **f32)
+        self.icv = torch.empty(L, d, **f32)
+        self.sink = torch.zeros(L, d, **f32)
+        self.losses = torch.zeros(4, **f32)
+        self.norm = torch.zeros(1, **f32)
+        self.kl_tea_row = torch.empty(B * T, dtype=torch.int32, device=device)
+        self.ce_label = torch.empty(B * T, dtype=torch.int64, device=device)
+        self.counts = torch.zeros(4, dtype=torch.int32, device=device)
+        self.ws = torch.zeros(self.lib.licv_kd_loss_workspace_bytes(B * T) + 64, dtype=torch.uint8,
+                              device=device)
+        self.opt_ws = torch.zeros(16, dtype=torch.uint8, device=device)
+        self.out = [torch.empty(B * T, d, dtype=dtype, device=device) for _ in range(L)]
+        self.dh = [torch.empty(B * T, d, dtype=dtype, device=device) for _ in range(L)]
+        self.dstu = torch.empty(B * T, V, dtype=dtype, device=device)
+        # the DeepSpeed recipe's fp16/bf16 chain: every op of the reference rounds
+        self.flags = (_abi.ROUND_Y | _abi.ROUND_NH | _abi.ROUND_NY | _abi.ROUND_T
+                      if dtype != torch.float32 else 0)
+        self.step_no = 0
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            self.abi.check(rc, what)
+
+    def step(self, batch, allreduce=True):
+        lib, st = self.lib, torch.cuda.current_stream().cuda_stream
+        L, d, V = CFG["layers"], CFG["d"], CFG["vocab"]
+        B, T = CFG["batch_per_gpu"], CFG["student_tokens"]
+        n_tok = B * T
+        p = self.param.data_ptr()
+        alpha_p, vec_p = p + 4 * self.n_vec, p
+        self._chk(lib.licv_icv_scale(alpha_p, vec_p, self.icv.data_ptr(), L, d,
+                                     int(CFG["use_sigmoid"]), st), "icv_scale")
+        for l in range(L):
+            self._chk(lib.licv_inject_fwd(batch["h"][l].data_ptr(), self.icv[l].data_ptr(),
+                                          self.out[l].data_ptr(), n_tok, d, self.code, self.code,
+                                          self.flags, st), "inject_fwd")
+        self._chk(lib.licv_kd_prepare_rows(
+            batch["ids"].data_ptr(), batch["qx"].data_ptr(), batch["att"].data_ptr(),
+            batch["t_ids"].data_ptr(), batch["t_len"].data_ptr(), 0, -1, 0, B, T,
+            CFG["kl_rows_per_sample"], self.kl_tea_row.data_ptr(), self.ce_label.data_ptr(),
+            self.counts.data_ptr(), st), "kd_prepare_rows")
+        self._chk(lib.licv_kd_loss_fwd_bwd(
+            batch["stu"].data_ptr(), self.dstu.data_ptr(), batch["tea"].data_ptr(),
+            self.kl_tea_row.data_ptr(), self.ce_label.data_ptr(), self.counts.data_ptr(), 0, 0,
+            CFG["temperature"], CFG["kl_eps"], CFG["hard_loss_weight"], 0, 1.0,
+            self.losses.data_ptr(), self.ws.data_ptr(), n_tok, V, V, V, self.code,
+            self.abi.ROUND_TEMPERED, st), "kd_loss")
+        self.sink.zero_()
+        for l in reversed(range(L)):
+            self._chk(lib.licv_inject_bwd(batch["h"][l].data_ptr(), batch["g"][l].data_ptr(),
+                                          self.icv[l].data_ptr(), self.dh[l].data_ptr(),
+                                          self.sink[l].data_ptr(), n_tok, d, self.code, self.code,
+                                          self.flags, st), "inject_bwd")
+        g = self.grad.data_ptr()
+        self._chk(lib.licv_icv_scale_bwd(alpha_p, vec_p, self.sink.data_ptr(), g,
+                                         g + 4 * self.n_vec, L, d, int(CFG["use_sigmoid"]), st),
+                  "icv_scale_bwd")
+        if self.world > 1 and allreduce:
+            # logged scalars ride in the tail of the same flat buffer (one collective per step)
+            self.grad[self.n_vec + self.n_alpha:self.n_vec + self.n_alpha + 3].copy_(self.losses[:3])
+            torch.distributed.all_reduce(self.grad)
+        self.step_no += 1
+        self._chk(lib.licv_adamw_step(p, g, self.m.data_ptr(), self.v.data_ptr(), self.n_vec,
+                                      self.n_alpha, 1e-4, 1e-2, 0.9, 0.999, 1e-8, 1e-3,
+                                      self.step_no, 1.0 / self.world, 1.0, self.norm.data_ptr(),
+                                      self.opt_ws.data_ptr(), st), "adamw_step")
+
+
+def time_kernel_launches(fn_list, stream):
+    """CUDA-event time around each launch (events on the launching stream) -> list of seconds."""
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in fn_list]
+    for (e0, e1), fn in zip(evs, fn_list):
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+    torch.cuda.synchronize()
+    return [e0.elapsed_time(e1) * 1e-3 for e0, e1 in evs]
+
+
+def load_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def esize(dtype):
+    return 4 if dtype == torch.float32 else 2
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's eager op chain on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_steps(n_steps, warmup, seed=0):
+    from oracle import torch_chain
+    torch.set_num_threads(os.cpu_count() or 1)
+    # bf16 on the CPU where the GPU recipe is fp16: fp16 eager kernels on CPU are not what any
+    # user of the reference would run, bf16 is (lmm_base.yaml precision "bf16")
+    dt = torch.bfloat16
+    batch = make_batch("cpu", seed, dt)
+    L, d, V = CFG["layers"], CFG["d"], CFG["vocab"]
+    B, T = CFG["batch_per_gpu"], CFG["student_tokens"]
+    alpha = torch.full((1, L), CFG["alpha_init_value"])
+    gen = torch.Generator().manual_seed(426)
+    vec = torch.randn(1, L, d, generator=gen) * 0.01
+    hs = [h.view(B, T, d) for h in batch["h"]]
+    gs = [g.view(B, T, d).float() for g in batch["g"]]   # fp32 ICV -> fp32 result -> fp32 grad
+    stu_mask = torch.zeros(B, T, dtype=torch.bool)
+    stu_mask[:, T - CFG["kl_rows_per_sample"]:] = True
+    temp = torch.tensor(CFG["temperature"])
+
+    def one():
+        return torch_chain.hot_path_step(hs, gs, alpha, vec, CFG["use_sigmoid"],
+                                         batch["stu"].view(B, T, V), batch["tea"], stu_mask,
+                                         batch["ids"], batch["att"], temp, CFG["kl_eps"],
+                                         CFG["hard_loss_weight"])
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        one()
+    dt_s = (time.perf_counter() - t0) / max(n_steps, 1)
+    return dt_s, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    steps = max(1, min(args.steps, 20))
+    warm = max(1, min(args.warmup, 3))
+    sec, cores = cpu_reference_steps(steps, warm)
+    val = CFG["batch_per_gpu"] / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 activations / fp32 ICV (CPU eager)",
+        "data": "synthetic", "config": dict(CFG, flush="inputs of one step (~290 MB) exceed L2"),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} full steps of the same workload (one 8-sample batch "
+                                   "each; rank 0 only, world-size independent) through "
+                                   "oracle/torch_chain.py, the reference's eager op chain + "
+                                   "autograd on the host CPU"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# main arm
+# ------------------------------------------------------------------------------------------------
+def bandwidth_shapes(hp, peak):
+    """configs[4]-sized launches of the same kernels: bandwidth-bound roofline points."""
+    lib, st = hp.lib, torch.cuda.current_stream().cuda_stream
+    out = []
+    d, V = CFG["d"], CFG["vocab"]
+    dt, code, es = hp.dtype, hp.code, esize(hp.dtype)
+    n_tok = 64 * 2048                                   # bs 64 x T 2048, 1 GiB in
+    h = [(torch.randn(n_tok, d, device=hp.device) * 4).to(dt) for _ in range(2)]
+    g = [torch.randn(n_tok, d, device=hp.device).to(dt) for _ in range(2)]
+    o = torch.empty(n_tok, d, dtype=dt, device=hp.device)
+    s = hp.icv[0]
+    ds = torch.zeros(d, device=hp.device)
+    for name, nbytes, fn in [
+        ("licv_inject_fwd", 2 * es * n_tok * d,
+         lambda i: lib.licv_inject_fwd(h[i % 2].data_ptr(), s.data_ptr(), o.data_ptr(), n_tok, d,
+                                       code, code, hp.flags, st)),
+        ("licv_inject_bwd", 3 * es * n_tok * d,
+         lambda i: lib.licv_inject_bwd(h[i % 2].data_ptr(), g[i % 2].data_ptr(), s.data_ptr(),
+                                       o.data_ptr(), ds.data_ptr(), n_tok, d, code, code, hp.flags,
+                                       st)),
+    ]:
+        for i in range(3):
+            fn(i)
+        ts = time_kernel_launches([lambda i=i: fn(i) for i in range(6)], torch.cuda.current_stream())
+        t = sum(ts) / len(ts)
+        out.append({"kernel": name, "shape": f"n_tok={n_tok} d={d} {CFG['dtype']}",
+                    "achieved": nbytes / t / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": nbytes / t / 1e9 / peak, "us": t * 1e6})
+    del h, g, o
+    R = 4096
+    stu = [(torch.randn(R, V, device=hp.device) * 3).to(dt) for _ in range(2)]
+    tea = [(torch.randn(R, V, device=hp.device) * 3).to(dt) for _ in range(2)]
+    dst = torch.empty(R, V, dtype=dt, device=hp.device)
+    lab = torch.randint(0, V, (R,), device=hp.device)
+    ws = torch.zeros(lib.licv_kd_loss_workspace_bytes(R) + 64, dtype=torch.uint8, device=hp.device)
+    losses = torch.zeros(4, device=hp.device)
+
+    def kd(i):
+        lib.licv_kd_loss_fwd_bwd(stu[i % 2].data_ptr(), dst.data_ptr(), tea[i % 2].data_ptr(), 0,
+                                 lab.data_ptr(), 0, R, R, 1.0, 1e-6, 0.5, 0, 1.0,
+                                 losses.data_ptr(), ws.data_ptr(), R, V, V, V, code, 16, st)
+
+    for i in range(2):
+        kd(i)
+    ts = time_kernel_launches([lambda i=i: kd(i) for i in range(4)], torch.cuda.current_stream())
+    t = sum(ts) / len(ts)
+    nbytes = 3 * es * R * V
+    out.append({"kernel": "licv_kd_loss_fwd_bwd", "shape": f"R={R} KL+CE rows V={V} {CFG['dtype']}",
+                "achieved": nbytes / t / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": nbytes / t / 1e9 / peak, "us": t * 1e6})
+    return out
+
+
+def run_e2e_host(hp, steps, warmup, seed):
+    """The step through the host-buffer entry points: inputs in pinned host memory, results back
+    in pinned host memory, all copies inside the timed region."""
+    import ctypes as C
+    lib = hp.lib
+    L, d, V = CFG["layers"], CFG["d"], CFG["vocab"]
+    B, T = CFG["batch_per_gpu"], CFG["student_tokens"]
+    n_tok, es = B * T, esize(hp.dtype)
+    hb = make_batch(hp.device, seed, hp.dtype, pinned_host=True)
+    out_h = [torch.empty(n_tok, d, dtype=hp.dtype).pin_memory() for _ in range(L)]
+    dh_h = [torch.empty(n_tok, d, dtype=hp.dtype).pin_memory() for _ in range(L)]
+    dstu_h = torch.empty(n_tok, V, dtype=hp.dtype).pin_memory()
+    ds_h = torch.zeros(L, d).pin_memory()
+    loss_h = torch.zeros(4).pin_memory()
+    icv_h = (hp.param[:L * d].view(L, d) * CFG["alpha_init_value"]).cpu().pin_memory()
+    # row lists are host-side integer work for a host plugin
+    T4 = CFG["kl_rows_per_sample"]
+    ktr = torch.full((n_tok,), -1, dtype=torch.int32)
+    lab = torch.full((n_tok,), -100, dtype=torch.int64)
+    ids = hb["ids"]
+    for b in range(B):
+        for k in range(T4):
+            ktr[b * T + T - T4 + k] = b * T4 + k
+        lab[b * T:b * T + T - 1] = ids[b, 1:]
+    ktr, lab = ktr.pin_memory(), lab.pin_memory()
+    n_kl, n_ce = int((ktr >= 0).sum()), int((lab != -100).sum())
+    sess = C.c_void_p()
+    scratch = max(3 * n_tok * d * es + 4 * d * 4 + 4096,
+                  (n_tok + B * T4) * V * es + n_tok * 16 + 65536) + (1 << 20)
+    hp.abi.check(lib.licv_host_session_create(C.byref(sess), scratch, 4), "host_session_create")
+
+    def step():
+        for l in range(L):
+            hp.abi.check(lib.licv_inject_fwd_host(sess, hb["h"][l].data_ptr(), icv_h[l].data_ptr(),
+                                                  out_h[l].data_ptr(), n_tok, d, hp.code, hp.code,
+                                                  hp.flags), "inject_fwd_host")
+        hp.abi.check(lib.licv_kd_loss_fwd_bwd_host(
+            sess, hb["stu"].data_ptr(), dstu_h.data_ptr(), hb["tea"].data_ptr(), ktr.data_ptr(),
+            lab.data_ptr(), n_kl, n_ce, CFG["temperature"], CFG["kl_eps"], CFG["hard_loss_weight"],
+            0, 1.0, loss_h.data_ptr(), n_tok, B * T4, V, hp.code, 16), "kd_loss_host")
+        for l in reversed(range(L)):
+            hp.abi.check(lib.licv_inject_bwd_host(sess, hb["h"][l].data_ptr(), hb["g"][l].data_ptr(),
+                                                  icv_h[l].data_ptr(), dh_h[l].data_ptr(),
+                                                  ds_h[l].data_ptr(), n_tok, d, hp.code, hp.code,
+                                                  hp.flags), "inject_bwd_host")
+        hp.abi.check(lib.licv_host_sync(sess), "host_sync")
+        return float(loss_h[2])   # the device->host read of the step's result
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    lib.licv_host_session_destroy(sess)
+    h2d = L * (2 * n_tok * d * es + 2 * d * 4) + (n_tok + B * T4) * V * es + n_tok * 12
+    d2h = L * (2 * n_tok * d * es + d * 4) + n_tok * V * es + 12
+    return dt, h2d, d2h
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip cpu_baseline / e2e / bandwidth-shape legs (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product has no CPU path "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=device)
+    dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[CFG["dtype"]]
+    hp = HotPath(device, dtype, world)
+    batch = make_batch(device, 1000 + rank, dtype)
+    peak, peak_src = load_peak()
+
+    stream = torch.cuda.Stream()
+    graph = None
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            hp.step(batch)
+        stream.synchronize()
+        if not args.no_graph:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                hp.step(batch)
+            for _ in range(3):
+                graph.replay()
+            stream.synchronize()
+
+        def barrier():
+            if world > 1:
+                torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with ClockSampler(local) as clocks:
+            e0.record(stream)
+            for _ in range(args.steps):
+                if graph is not None:
+                    graph.replay()
+                else:
+                    hp.step(batch)
+            e1.record(stream)
+            barrier()
+        sec = e0.elapsed_time(e1) * 1e-3
+        if world > 1:
+            t = torch.tensor([sec], device=device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            sec = float(t)
+        ms_per_step = sec / args.steps * 1e3
+        value = CFG["batch_per_gpu"] * world / (sec / args.steps)
+
+        # ---- dominant kernel, per launch, CUDA events on the launching stream -------------------
+        L, d = CFG["layers"], CFG["d"]
+        n_tok = CFG["batch_per_gpu"] * CFG["student_tokens"]
+        es = esize(dtype)
+        st = stream.cuda_stream
+        hp.sink.zero_()
+
+        def bwd_launch(l):
+            return lambda: hp.lib.licv_inject_bwd(batch["h"][l].data_ptr(), batch["g"][l].data_ptr(),
+                                                  hp.icv[l].data_ptr(), hp.dh[l].data_ptr(),
+                                                  hp.sink[l].data_ptr(), n_tok, d, hp.code, hp.code,
+                                                  hp.flags, st)
+
+        def fwd_launch(l):
+            return lambda: hp.lib.licv_inject_fwd(batch["h"][l].data_ptr(), hp.icv[l].data_ptr(),
+                                                  hp.out[l].data_ptr(), n_tok, d, hp.code, hp.code,
+                                                  hp.flags, st)
+
+        time_kernel_launches([bwd_launch(l) for l in range(L)], stream)      # warm
+        tb = time_kernel_launches([bwd_launch(l) for l in reversed(range(L))], stream)
+        tf = time_kernel_launches([fwd_launch(l) for l in range(L)], stream)
+        t_bwd = sum(tb) / len(tb)
+        bytes_bwd = 3 * es * n_tok * d
+        roofline = {"bound": "hbm", "kernel": "licv_inject_bwd",
+                    "achieved": bytes_bwd / t_bwd / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": bytes_bwd / t_bwd / 1e9 / peak, "traffic": None,
+                    "peak_source": peak_src, "bytes_per_launch": bytes_bwd,
+                    "us_per_launch": t_bwd * 1e6, "launches_per_step": L,
+                    "share_of_step": L * t_bwd / (ms_per_step * 1e-3),
+                    "how": "CUDA events around each of the 32 launches on the launching stream, "
+                           "eager pass right after the timed region (the timed region itself is "
+                           "one CUDA graph per step); 256 tokens per launch = 6 MB: latency-bound",
+                    "fwd_us_per_launch": sum(tf) / len(tf) * 1e6}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": CFG["dtype"] + " (fp32 accumulate)",
+        "data": "synthetic",
+        "config": dict(CFG, global_batch=CFG["batch_per_gpu"] * world, parallelism=f"dp{world}",
+                       cuda_graph=graph is not None,
+                       flush="inputs of one step (~290 MB, a distinct buffer per layer) exceed L2"),
+        "roofline": roofline, "clocks": clocks.summary(),
+        "gpu_launches": (HotPath.LAUNCHES_PER_STEP) * args.steps,
+    }
+
+    if rank == 0 and not args.no_extras:
+        with torch.cuda.stream(stream):
+            line["roofline_bw"] = bandwidth_shapes(hp, peak)
+        stream.synchronize()
+    if not args.no_extras:
+        e_steps = max(3, min(args.steps, 20))
+        e_sec, h2d, d2h = run_e2e_host(hp, e_steps, 2, 1000 + rank)
+        if world > 1:
+            t = torch.tensor([e_sec], device=device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            e_sec = float(t)
+        line["e2e"] = {"value": CFG["batch_per_gpu"] * world / e_sec, "unit": UNIT,
+                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "ms_per_step": e_sec * 1e3, "steps": e_steps,
+                       "how": "licv_*_host entry points on a 4-slot session: pinned host inputs, "
+                              "pinned host results, copies inside the timed region"}
+    if rank == 0 and world == 1 and not args.no_extras:
+        one, cores = cpu_reference_steps(1, 1)
+        n = max(2, min(40, int(12.0 / max(one, 1e-3))))
+        sec_cpu, cores = cpu_reference_steps(n, 0)
+        line["cpu_baseline"] = {"value": CFG["batch_per_gpu"] / sec_cpu, "unit": UNIT,
+                                "cores": cores, "kind": "port", "ms_per_step": sec_cpu * 1e3,
+                                "sample": f"{n} full steps of the same workload through "
+                                          "oracle/torch_chain.py (the reference's eager op chain "
+                                          "+ autograd, bf16 activations, fp32 ICV) on the host CPU"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -17,7 +17,8 @@ def main():
     d, V = 4096, 32002
     s = torch.randn(d, device="cuda")
     ds = torch.zeros(d, device="cuda")
-    for n_tok in (32768, 256):
+    toks = [int(x) for x in os.environ.get("LICV_PROFILE_TOKENS", "32768,256").split(",")]
+    for n_tok in toks:
         h = (torch.randn(n_tok, d, device="cuda") * 4).to(dt)
         g = torch.randn(n_tok, d, device="cuda").to(dt)
         o = torch.empty_like(h)

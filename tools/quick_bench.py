@@ -1,84 +1,124 @@
-"""Quick kernel timing sweep (CUDA events, rotating buffers larger than L2)."""
+"""Kernel timing sweep through the C ABI (CUDA events around CUDA-graph replays; rotating buffers
+larger than L2, so every launch streams from HBM).
+
+    python tools/quick_bench.py [inject] [kd] [--dtype bf16|fp16] [--tokens 256,131072] [--rows 32,2048]
+"""
+import argparse
 import json
-import sys
 import os
+import sys
 
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from licv_vqa_b200 import ops  # noqa: E402
+from licv_vqa_b200 import _abi  # noqa: E402
+
+PEAK = 6549.4
+try:
+    PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                       "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
 
 
-def timeit(fn, n_iter=20, warm=3):
-    for _ in range(warm):
-        fn(0)
-    torch.cuda.synchronize()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(n_iter):
-        fn(i)
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n_iter * 1e-3
+def time_graph(launch, nbuf, reps=5):
+    """launch(k) enqueues one kernel on buffer set k; returns seconds per launch."""
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for k in range(nbuf):
+            launch(k)
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for k in range(nbuf):
+                launch(k)
+        for _ in range(3):
+            g.replay()
+        s.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(reps):
+            g.replay()
+        e1.record(s)
+        s.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / (reps * nbuf)
 
 
 def main():
-    peak = 6549.4
-    res = []
-    d = 4096
-    for n_tok in [24, 256, 2048, 16384, 65536, 131072]:
-        nbuf = max(2, min(32, int(400e6 // (n_tok * d * 2)) + 1))
-        hs = [(torch.randn(n_tok, d, device="cuda") * 4).bfloat16() for _ in range(nbuf)]
-        gs = [torch.randn(n_tok, d, device="cuda").bfloat16() for _ in range(nbuf)]
-        outs = [torch.empty_like(hs[0]) for _ in range(nbuf)]
-        s = torch.randn(d, device="cuda")
-        ds = torch.zeros(d, device="cuda")
-        from licv_vqa_b200 import _abi
-        lib = _abi.load()
-        st = torch.cuda.current_stream().cuda_stream
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", nargs="*", default=["inject", "kd"])
+    ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--tokens", default="24,256,2048,16384,65536,131072")
+    ap.add_argument("--rows", default="32,256,2048,8192")
+    ap.add_argument("--vocab", type=int, default=32002)
+    ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--d", type=int, default=4096)
+    args = ap.parse_args()
+    dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
+    code = {"bf16": _abi.BF16, "fp16": _abi.F16, "fp32": _abi.F32}[args.dtype]
+    e = 4 if args.dtype == "fp32" else 2
+    lib = _abi.load()
+    d = args.d
+    if "inject" in args.which:
+        for n_tok in [int(x) for x in args.tokens.split(",")]:
+            nbuf = max(2, min(32, int(600e6 // (n_tok * d * e * 3)) + 1))
+            hs = [(torch.randn(n_tok, d, device="cuda") * 4).to(dt) for _ in range(nbuf)]
+            gs = [torch.randn(n_tok, d, device="cuda").to(dt) for _ in range(nbuf)]
+            outs = [torch.empty_like(hs[0]) for _ in range(nbuf)]
+            s = torch.randn(d, device="cuda")
+            ds = torch.zeros(d, device="cuda")
 
-        def fwd(i):
-            k = i % nbuf
-            lib.licv_inject_fwd(hs[k].data_ptr(), s.data_ptr(), outs[k].data_ptr(), n_tok, d, 1, 1, 0, st)
+            def fwd(k):
+                st = torch.cuda.current_stream().cuda_stream
+                _abi.check(lib.licv_inject_fwd(hs[k].data_ptr(), s.data_ptr(), outs[k].data_ptr(),
+                                               n_tok, d, code, code, args.flags, st))
 
-        def bwd(i):
-            k = i % nbuf
-            lib.licv_inject_bwd(hs[k].data_ptr(), gs[k].data_ptr(), s.data_ptr(), outs[k].data_ptr(),
-                                ds.data_ptr(), n_tok, d, 1, 1, 0, st)
+            def bwd(k):
+                st = torch.cuda.current_stream().cuda_stream
+                _abi.check(lib.licv_inject_bwd(hs[k].data_ptr(), gs[k].data_ptr(), s.data_ptr(),
+                                               outs[k].data_ptr(), ds.data_ptr(), n_tok, d, code,
+                                               code, args.flags, st))
 
-        tf = timeit(fwd, 50)
-        tb = timeit(bwd, 50)
-        res.append(dict(kernel="inject_fwd", n_tok=n_tok, us=tf * 1e6, gbs=4 * n_tok * d / tf / 1e9,
-                        frac=4 * n_tok * d / tf / 1e9 / peak))
-        res.append(dict(kernel="inject_bwd", n_tok=n_tok, us=tb * 1e6, gbs=6 * n_tok * d / tb / 1e9,
-                        frac=6 * n_tok * d / tb / 1e9 / peak))
-        del hs, gs, outs
-    V = 32002
-    for R in [32, 256, 2048, 8192]:
-        nbuf = max(2, min(8, int(400e6 // (R * V * 2)) + 1))
-        stus = [(torch.randn(R, V, device="cuda") * 3).bfloat16() for _ in range(nbuf)]
-        teas = [(torch.randn(R, V, device="cuda") * 3).bfloat16() for _ in range(nbuf)]
-        lab = torch.randint(0, V, (R,), device="cuda")
+            for name, fn, nb in (("inject_fwd", fwd, 2 * e), ("inject_bwd", bwd, 3 * e)):
+                t = time_graph(fn, nbuf)
+                gbs = nb * n_tok * d / t / 1e9
+                print(json.dumps(dict(kernel=name, n_tok=n_tok, d=d, dtype=args.dtype,
+                                      us=round(t * 1e6, 2), gbs=round(gbs, 1),
+                                      frac=round(gbs / PEAK, 4))), flush=True)
+            del hs, gs, outs
+    if "kd" in args.which:
+        V = args.vocab
+        for R in [int(x) for x in args.rows.split(",")]:
+            nbuf = max(2, min(8, int(600e6 // (R * V * e * 3)) + 1))
+            stus = [(torch.randn(R, V, device="cuda") * 3).to(dt) for _ in range(nbuf)]
+            teas = [(torch.randn(R, V, device="cuda") * 3).to(dt) for _ in range(nbuf)]
+            dst = [torch.empty_like(stus[0]) for _ in range(nbuf)]
+            lab = torch.randint(0, V, (R,), device="cuda")
+            ws = torch.zeros(lib.licv_kd_loss_workspace_bytes(R) + 64, dtype=torch.uint8,
+                             device="cuda")
+            losses = torch.zeros(4, device="cuda")
 
-        def kd(i):
-            k = i % nbuf
-            ops.kd_loss_raw(stus[k], teas[k], None, lab, None, R, R, 1.0, 1e-6, 0.5, in_place=True)
+            def kd(k):
+                st = torch.cuda.current_stream().cuda_stream
+                _abi.check(lib.licv_kd_loss_fwd_bwd(
+                    stus[k].data_ptr(), dst[k].data_ptr(), teas[k].data_ptr(), 0, lab.data_ptr(),
+                    0, R, R, 1.0, 1e-6, 0.5, 0, 1.0, losses.data_ptr(), ws.data_ptr(), R, V, V, V,
+                    code, 16, st))
 
-        def kd_ce(i):
-            k = i % nbuf
-            ops.kd_loss_raw(stus[k], None, None, lab, None, 0, R, 1.0, 1e-6, 0.5, only_hard_loss=True,
-                            in_place=True)
+            def kd_ce(k):
+                st = torch.cuda.current_stream().cuda_stream
+                _abi.check(lib.licv_kd_loss_fwd_bwd(
+                    stus[k].data_ptr(), dst[k].data_ptr(), 0, 0, lab.data_ptr(), 0, 0, R, 1.0,
+                    1e-6, 0.5, 1, 1.0, losses.data_ptr(), ws.data_ptr(), R, V, V, V, code, 16, st))
 
-        t = timeit(kd, 10)
-        res.append(dict(kernel="kd_loss kl+ce", R=R, us=t * 1e6, gbs=6 * R * V / t / 1e9,
-                        frac=6 * R * V / t / 1e9 / peak))
-        t = timeit(kd_ce, 10)
-        res.append(dict(kernel="kd_loss ce-only", R=R, us=t * 1e6, gbs=4 * R * V / t / 1e9,
-                        frac=4 * R * V / t / 1e9 / peak))
-        del stus, teas
-    for r in res:
-        print(json.dumps(r))
+            for name, fn, nb in (("kd_loss kl+ce", kd, 3 * e), ("kd_loss ce-only", kd_ce, 2 * e)):
+                t = time_graph(fn, nbuf)
+                gbs = nb * R * V / t / 1e9
+                print(json.dumps(dict(kernel=name, R=R, V=V, dtype=args.dtype,
+                                      us=round(t * 1e6, 2), gbs=round(gbs, 1),
+                                      frac=round(gbs / PEAK, 4))), flush=True)
+            del stus, teas, dst
 
 
 if __name__ == "__main__":

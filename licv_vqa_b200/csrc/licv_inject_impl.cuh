@@ -106,9 +106,44 @@ int launch_bwd_pipe(const Args& a, const Launch& L) {
     pa.n_stages = stages;
     pa.n_batches = (L.n_tok + TB - 1) / TB;
     static const int per_sm = env_int("LICV_PIPE_CTAS_PER_SM", 2);
-    const int64_t cap = (int64_t)per_sm * device_info().sm_count;
-    kern<<<(int)(pa.n_batches < cap ? pa.n_batches : cap), kPipeThreads, smem, L.stream>>>(pa);
-    return (int)cudaGetLastError();
+    static const int cluster = env_int("LICV_PIPE_CLUSTER", 4);   // 1, 2, 4 or 8
+    // a cluster launch and its two cluster barriers cost ~1 us: only worth it once enough CTAs
+    // would otherwise queue on the same d_shift addresses
+    const int C = ((cluster == 2 || cluster == 4 || cluster == 8) && pa.n_batches > 32) ? cluster : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kPipeThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = L.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = C > 1 ? 1 : 0;
+    // resident CTAs: whole clusters that fit the device at once
+    static int64_t cap = 0;
+    static size_t cap_smem = 0;
+    static int cap_c = 0;
+    if (cap == 0 || cap_smem != smem || cap_c != C) {
+        int n_clusters = 0;
+        cfg.gridDim = dim3(C * device_info().sm_count);
+        if (C > 1 && cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg) == cudaSuccess &&
+            n_clusters > 0) {
+            cap = (int64_t)n_clusters * C;
+        } else {
+            cudaGetLastError();
+            cap = (int64_t)per_sm * device_info().sm_count / C * C;
+        }
+        const int64_t want = (int64_t)per_sm * device_info().sm_count;
+        if (cap > want) cap = want / C * C;
+        cap_smem = smem;
+        cap_c = C;
+    }
+    int64_t grid = pa.n_batches < cap ? pa.n_batches : cap;
+    grid = (grid + C - 1) / C * C;
+    cfg.gridDim = dim3((unsigned)grid);
+    return (int)cudaLaunchKernelEx(&cfg, kern, pa);
 }
 
 template <int HDT, int GDT, int VPT, int RND>

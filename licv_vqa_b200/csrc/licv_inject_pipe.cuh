@@ -78,6 +78,36 @@ __device__ __forceinline__ uint4 lds128(const void* p) {
     return r;
 }
 
+
+// ---- thread-block cluster helpers (distributed shared memory) --------------------------------
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_num_ctas() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                 "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dsmem_addr(const void* p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr));
+    return v;
+}
+
 struct PipeArgs {
     Args a;
     int n_stages;
@@ -234,14 +264,46 @@ __global__ void __launch_bounds__(kPipeThreads, 3) bwd_pipe_kernel(PipeArgs pa) 
         }
     }
 
+    // d_shift.  The L2 atomic units retire about one fp32 add per clock per slice and a row of
+    // d_shift lives in few slices, so what costs is the NUMBER of CTAs that add: the CTAs of a
+    // thread-block cluster first sum their rows through distributed shared memory (CTA r of C
+    // sums columns [r d/C, (r+1) d/C) of all C rows), then each issues REDG.F32x4 for its
+    // columns only: C times fewer atomics.
+    const uint32_t C = cluster_num_ctas();
+    if (C == 1) {
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) {
+            const int j = tid + k * kPipeThreads;
+#pragma unroll
+            for (int e = 0; e < EPV; e += 4)
+                red_add_v4(a.d_shift + (int64_t)j * EPV + e, ds[k][e], ds[k][e + 1], ds[k][e + 2],
+                           ds[k][e + 3]);
+        }
+        return;
+    }
+    constexpr int kRowF4 = VPT * kPipeThreads * EPV / 4;    // float4s in one d_shift row
+    float4* row = reinterpret_cast<float4*>(ring);           // every stage has been consumed
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
         const int j = tid + k * kPipeThreads;
 #pragma unroll
         for (int e = 0; e < EPV; e += 4)
-            red_add_v4(a.d_shift + (int64_t)j * EPV + e, ds[k][e], ds[k][e + 1], ds[k][e + 2],
-                       ds[k][e + 3]);
+            row[(j * EPV + e) / 4] = make_float4(ds[k][e], ds[k][e + 1], ds[k][e + 2], ds[k][e + 3]);
     }
+    cluster_sync_all();
+    const uint32_t rank = cluster_cta_rank();
+    const int per = kRowF4 / (int)C;   // C divides kRowF4 (C is 2, 4 or 8)
+    for (int i = tid; i < per; i += kPipeThreads) {
+        const int q = (int)rank * per + i;
+        float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t r = 0; r < C; ++r) {
+            const float4 v = ld_dsmem_f4(dsmem_addr(row + q, r));
+            tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
+        }
+        red_add_v4(a.d_shift + (int64_t)q * 4, tot.x, tot.y, tot.z, tot.w);
+    }
+    cluster_sync_all();   // no CTA may exit while a peer still reads its row
 }
 
 }  // namespace inject

@@ -46,6 +46,7 @@ def _digest():
     files = _sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)
                                 if f.endswith((".cuh", ".h")))
     files += [os.path.join(INCLUDE, "licv_b200.h"), os.path.abspath(__file__)]
+    h.update(os.environ.get("LICV_EXTRA_NVCC_FLAGS", "").encode())
     for f in files:
         h.update(f.encode())
         with open(f, "rb") as fh:
@@ -68,7 +69,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(obj_dir, exist_ok=True)
     for src in _sources():
         obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj]
+        extra = os.environ.get("LICV_EXTRA_NVCC_FLAGS", "").split()   # e.g. -DLICV_TRACE (debug)
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj]
         procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE,
                                                  stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

@@ -15,8 +15,8 @@
 // makes the gradient need W_n, i.e. a full sweep, before the first gradient element can be
 // written) re-read it through L2 where it is still resident (a row is 64-128 KB, L2 is 126 MB).
 // HBM traffic is therefore the algorithmic 3 e V bytes per KL row (2 e V for a CE-only row),
-// and dstu may alias stu.  licv_kd_loss_cluster.cu holds the register-resident cluster kernel
-// the dispatcher prefers when the rows qualify.
+// and dstu may alias stu.  licv_kd_loss_cluster.cu holds the cluster kernel (every exponential
+// evaluated once, rows cached on chip) that the dispatcher prefers when a row fits a cluster.
 #include "licv_common.cuh"
 #include "licv_kd_loss.cuh"
 
@@ -377,6 +377,9 @@ extern "C" int licv_kd_loss_fwd_bwd(const void* stu, void* dstu, const void* tea
     a.n_rows = n_rows; a.vocab = vocab; a.stu_stride = stu_stride; a.tea_stride = tea_stride;
     a.round_flags = round_flags;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int C = 0, NV = 0;
+    if (kd_cluster_plan(vocab, dtype, temperature, ce_label != nullptr && !only_hard_loss, &C, &NV))
+        return launch_kd_cluster(a, dtype, C, NV, st);
     return launch_kd_generic(a, dtype, st);
 }
 

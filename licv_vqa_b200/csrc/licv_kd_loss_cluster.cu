@@ -1,0 +1,778 @@
+// L-ICV distillation loss, cluster kernel: ONE pass over HBM, every transcendental evaluated once.
+//
+// Same arithmetic as the generic kernel in licv_kd_loss.cu (reference icv_src/icv_module.py:
+// 121-134 for the KL, the HF-internal shifted CE consumed at :94-98,115-117, the combine at
+// :100-101,107-119); what changes is where a row lives between its three sweeps.
+//
+// The kl_eps inside the logarithms makes d(stu) depend on W_n = sum_v p q/(q+eps), so a row needs
+// (1) its softmax partition sums, (2) the KL value and W_n, (3) the gradient: three sweeps with
+// two row-wide reductions between them.  The generic kernel re-reads the 16-bit logits from L2
+// for every sweep and re-evaluates both exponentials each time (~9 MUFU per element: the SFU
+// pipe, not HBM, bounds it at ~20 % of the roofline).  Here a row pair is spread over a
+// thread-block CLUSTER (C CTAs x 256 threads, C x NV x 256 16-byte vectors >= one row):
+//
+//   sweep B  registers (raw logits, prefetched during the previous row) -> e = 2^(u - m_thread)
+//            for student and teacher, written as fp32 to a thread-private shared-memory cache
+//            (each thread only ever reads back its own slots: no barrier, no bank conflicts);
+//            the softmax sums are carried as online-softmax (max, sum) pairs, so ONE reduction
+//            yields max and partition sum of both rows;
+//   sweep C  cache -> p, q, the KL terms and w = p q/(q+eps); kl_w * w overwrites the teacher
+//            slot;  second reduction: (KL_n, W_n);
+//   sweep D  cache -> gradient = e_s A - kl_w w - ce_w [j = label], packed and stored.
+//
+// 4 MUFU per element (2 ex2, 1 rcp, 1 lg2) instead of 9, HBM traffic = the algorithmic 3 e V
+// bytes per KL row (2 e V for a CE-only row, e V zero-fill for a row in neither loss).  The two
+// reductions cross the cluster through distributed shared memory (st.shared::cluster +
+// barrier.cluster).  Three CTAs of different clusters share an SM, so one row's reductions and
+// loads overlap another's arithmetic; the next row's logits are requested before the first
+// reduction of the current one.
+//
+// Rows may start on any element boundary (V = 32002 / 32003): the student row is walked in
+// 16-byte-aligned vectors, partial first/last vectors go element by element, the teacher row is
+// read with the widest loads its relative phase allows.
+//
+// Not a dense contraction: no tensor cores; bounds are HBM, then the SFU and FMA pipes.
+#include <cstdlib>
+
+#include "licv_common.cuh"
+#include "licv_kd_loss.cuh"
+
+namespace licv {
+namespace {
+
+constexpr int kT = 256;
+constexpr int kWarps = kT / 32;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kNoMax = -3.0e38f;   // "no element yet": finite, so differences never give NaN
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_num_ctas() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                 "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// mbarrier in this CTA's shared memory, completed by bytes that peers write with st.async
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LICV_KD_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LICV_KD_DONE;\n"
+        "bra LICV_KD_WAIT;\n"
+        "LICV_KD_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 16 bytes into slot `local` of CTA `rank`, counted on that CTA's mbarrier `bar`: a one-way
+// message, no fence and no round trip (a release at cluster scope would wait for this warp's
+// earlier gradient stores to drain)
+__device__ __forceinline__ void st_async_f4(const void* local, const uint64_t* bar, uint32_t rank,
+                                            float4 v) {
+    uint32_t addr, mbar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(addr) : "r"(smem_u32(local)), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(mbar) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile(
+        "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1,%2,%3,%4}, [%5];" ::
+            "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(mbar)
+        : "memory");
+}
+// -inf in the storage format, as a 16-byte vector (masks elements outside the row)
+template <int DT> __device__ __forceinline__ uint32_t neg_inf_word();
+template <> __device__ __forceinline__ uint32_t neg_inf_word<LICV_F32>() { return 0xff800000u; }
+template <> __device__ __forceinline__ uint32_t neg_inf_word<LICV_BF16>() { return 0xff80ff80u; }
+template <> __device__ __forceinline__ uint32_t neg_inf_word<LICV_F16>() { return 0xfc00fc00u; }
+
+// raw element bits <-> position inside a 16-byte vector
+template <int DT>
+__device__ __forceinline__ void put_elem(uint4& v, int e, uint32_t bits) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+    if (Fmt<DT>::kBytes == 4) {
+        w[e] = bits;
+    } else {
+        const int sh = (e & 1) * 16;
+        w[e >> 1] = (w[e >> 1] & ~(0xffffu << sh)) | (bits << sh);
+    }
+}
+template <int DT>
+__device__ __forceinline__ uint32_t load_bits(const char* row, int64_t j) {
+    if (Fmt<DT>::kBytes == 4) return reinterpret_cast<const uint32_t*>(row)[j];
+    return reinterpret_cast<const uint16_t*>(row)[j];
+}
+
+// One 16-byte vector's worth of elements j0 .. j0+EPV-1 of a row (elements outside [0, V) read
+// as -inf).  `align`: guaranteed alignment in bytes of (row + j0 * EB) for interior vectors.
+template <int DT>
+__device__ __forceinline__ uint4 load_row_vec(const char* row, int j0, int V, int align) {
+    constexpr int EPV = Fmt<DT>::kPerVec;
+    constexpr int EB = Fmt<DT>::kBytes;
+    const uint32_t ninf = neg_inf_word<DT>();
+    uint4 v = make_uint4(ninf, ninf, ninf, ninf);
+    if (j0 >= V || j0 + EPV <= 0) return v;
+    const char* p = row + (int64_t)j0 * EB;
+    if (j0 >= 0 && j0 + EPV <= V) {
+        if (align >= 16) {
+            v = ld_stream(reinterpret_cast<const uint4*>(p));
+        } else if (align >= 8) {
+            const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
+            const uint2 b = __ldg(reinterpret_cast<const uint2*>(p) + 1);
+            v = make_uint4(a.x, a.y, b.x, b.y);
+        } else if (align >= 4) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+            v = make_uint4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+        } else {
+            const uint16_t* q = reinterpret_cast<const uint16_t*>(p);
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                w[i] = (uint32_t)__ldg(q + 2 * i) | ((uint32_t)__ldg(q + 2 * i + 1) << 16);
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        return v;
+    }
+    // first / last vector of the row: element by element
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) {
+        const int j = j0 + e;
+        if (j >= 0 && j < V) put_elem<DT>(v, e, load_bits<DT>(row, j));
+    }
+    return v;
+}
+
+template <int DT>
+__device__ __forceinline__ void store_row_vec(char* row, int j0, int V, bool vec_ok, const float* f) {
+    constexpr int EPV = Fmt<DT>::kPerVec;
+    constexpr int EB = Fmt<DT>::kBytes;
+    if (j0 >= V || j0 + EPV <= 0) return;
+    if (vec_ok && j0 >= 0 && j0 + EPV <= V) {
+        st_vec(reinterpret_cast<uint4*>(row + (int64_t)j0 * EB), pack<DT>(f));
+        return;
+    }
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) {
+        const int j = j0 + e;
+        if (j >= 0 && j < V) store_elem<DT>(row, j, f[e]);
+    }
+}
+
+// running maximum over the raw storage words of a vector
+template <int DT> struct RawMax;
+template <> struct RawMax<LICV_F32> {
+    float m = -INFINITY;
+    __device__ __forceinline__ void add(const uint4& v) {
+        m = fmaxf(fmaxf(m, __uint_as_float(v.x)), fmaxf(__uint_as_float(v.y), __uint_as_float(v.z)));
+        m = fmaxf(m, __uint_as_float(v.w));
+    }
+    __device__ __forceinline__ float get() const { return m; }
+};
+template <> struct RawMax<LICV_BF16> {
+    __nv_bfloat162 m;
+    __device__ __forceinline__ RawMax() {
+        const uint32_t w = 0xff80ff80u;
+        m = *reinterpret_cast<const __nv_bfloat162*>(&w);
+    }
+    __device__ __forceinline__ void add(const uint4& v) {
+        const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+        m = __hmax2(__hmax2(m, p[0]), __hmax2(p[1], __hmax2(p[2], p[3])));
+    }
+    __device__ __forceinline__ float get() const {
+        return fmaxf(__bfloat162float(m.x), __bfloat162float(m.y));
+    }
+};
+template <> struct RawMax<LICV_F16> {
+    __half2 m;
+    __device__ __forceinline__ RawMax() {
+        const uint32_t w = 0xfc00fc00u;
+        m = *reinterpret_cast<const __half2*>(&w);
+    }
+    __device__ __forceinline__ void add(const uint4& v) {
+        const __half2* p = reinterpret_cast<const __half2*>(&v);
+        m = __hmax2(__hmax2(m, p[0]), __hmax2(p[1], __hmax2(p[2], p[3])));
+    }
+    __device__ __forceinline__ float get() const {
+        return fmaxf(__half2float(m.x), __half2float(m.y));
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Cluster-wide reductions without a CTA barrier and without a serial section: every WARP sends
+// its partial (16 bytes) straight to every CTA of the cluster (st.async, counted on the
+// receiver's mbarrier); the receiver's warps each read the C x 8 partials (one or two per lane)
+// and finish with a shuffle reduction.  A row's softmax statistics travel as online-softmax
+// pairs (m, z): sum_j 2^(u_j) = z 2^m with m an INTEGER, so rescaling to a common maximum is an
+// exponent-field operation on the ALU pipe - the joins cost no MUFU.
+// ---------------------------------------------------------------------------------------------
+constexpr int kNoMaxI = -(1 << 20);   // "no element": any real maximum wins, scale factor 0
+
+// 2^k for an integer k <= 0 (0 below the normal range)
+__device__ __forceinline__ float pow2i(int k) {
+    const int e = k + 127;
+    return __int_as_float((e > 0 ? e : 0) << 23);
+}
+struct MZ2 {
+    int ms;
+    float zs;
+    int mt;
+    float zt;
+};
+__device__ __forceinline__ MZ2 mz_join(const MZ2& a, const MZ2& b) {
+    MZ2 r;
+    r.ms = a.ms > b.ms ? a.ms : b.ms;
+    r.mt = a.mt > b.mt ? a.mt : b.mt;
+    r.zs = fmaf(a.zs, pow2i(a.ms - r.ms), b.zs * pow2i(b.ms - r.ms));
+    r.zt = fmaf(a.zt, pow2i(a.mt - r.mt), b.zt * pow2i(b.mt - r.mt));
+    return r;
+}
+__device__ __forceinline__ MZ2 mz_warp(MZ2 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MZ2 b;
+        b.ms = __shfl_xor_sync(0xffffffffu, v.ms, o);
+        b.zs = __shfl_xor_sync(0xffffffffu, v.zs, o);
+        b.mt = __shfl_xor_sync(0xffffffffu, v.mt, o);
+        b.zt = __shfl_xor_sync(0xffffffffu, v.zt, o);
+        v = mz_join(v, b);
+    }
+    return v;
+}
+
+struct Exchange {
+    float4* slots;      // [C * kWarps] partials in THIS CTA's shared memory
+    uint64_t* bar;      // completes when C * kWarps * 16 bytes have arrived
+    uint32_t parity;
+};
+
+// this warp's partial -> slot (rank, warp) of every CTA of the cluster
+__device__ __forceinline__ void exchange_send(const Exchange& x, float4 v, uint32_t rank, uint32_t C) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) mbar_expect_tx(x.bar, C * kWarps * 16u);
+    if ((uint32_t)lane < C) st_async_f4(x.slots + rank * kWarps + warp, x.bar, (uint32_t)lane, v);
+}
+__device__ __forceinline__ MZ2 exchange_recv_mz(Exchange& x, uint32_t C) {
+    const int lane = threadIdx.x & 31;
+    mbar_wait(x.bar, x.parity);
+    x.parity ^= 1u;
+    const int n = (int)C * kWarps;
+    MZ2 v{kNoMaxI, 0.f, kNoMaxI, 0.f};
+    if (lane < n) {
+        const float4 p = x.slots[lane];
+        v = MZ2{__float_as_int(p.x), p.y, __float_as_int(p.z), p.w};
+    }
+    if (lane + 32 < n) {
+        const float4 p = x.slots[lane + 32];
+        v = mz_join(v, MZ2{__float_as_int(p.x), p.y, __float_as_int(p.z), p.w});
+    }
+    return mz_warp(v);
+}
+__device__ __forceinline__ float2 exchange_recv_sum(Exchange& x, uint32_t C) {
+    const int lane = threadIdx.x & 31;
+    mbar_wait(x.bar, x.parity);
+    x.parity ^= 1u;
+    const int n = (int)C * kWarps;
+    float2 v = make_float2(0.f, 0.f);
+    if (lane < n) {
+        const float4 p = x.slots[lane];
+        v = make_float2(p.x, p.y);
+    }
+    if (lane + 32 < n) {
+        const float4 p = x.slots[lane + 32];
+        v.x += p.x;
+        v.y += p.y;
+    }
+    v.x = warp_sum(v.x);
+    v.y = warp_sum(v.y);
+    return v;
+}
+
+#ifdef LICV_TRACE
+// debug build only: phase timestamps (clock64) of one thread of the first CTAs, 8 per row
+__device__ long long g_trace[64 * 64 * 8];
+#define LICV_TP(slot)                                                                      \
+    do {                                                                                   \
+        if (tid == LICV_TRACE_TID && blockIdx.x < 64 && trace_row < 64)                    \
+            g_trace[(blockIdx.x * 64 + trace_row) * 8 + (slot)] = clock64();               \
+    } while (0)
+#ifndef LICV_TRACE_TID
+#define LICV_TRACE_TID 0
+#endif
+#else
+#define LICV_TP(slot) do { } while (0)
+#endif
+
+constexpr int kLabNone = -100;            // not a CE row
+constexpr int kLabBad = 0x7fffffff;       // a label outside int32: out of range for any V
+
+template <int DT, int NV>
+__global__ void __launch_bounds__(kT, (NV <= 4 ? 3 : 1)) kd_loss_cluster_kernel(KdArgs a) {
+    constexpr int EPV = Fmt<DT>::kPerVec;
+    constexpr int EB = Fmt<DT>::kBytes;
+    constexpr int Q = EPV / 4;                      // float4 slots per vector
+    constexpr int kStep = kT * EPV;                 // elements between a thread's vectors
+    extern __shared__ __align__(16) float4 cache[];  // [2][NV * Q][kT]: e_s then e_t / kl_w * w
+    __shared__ __align__(16) float4 slots[3][8 * kWarps];   // reduction 1 (two row parities), reduction 2
+    __shared__ __align__(8) uint64_t xbar[2];
+    __shared__ float s_tot[2 * kWarps];
+    __shared__ int s_last;
+
+    float4* const cs = cache;
+    float4* const ct = cache + NV * Q * kT;
+    const int tid = threadIdx.x;
+    const uint32_t C = cluster_num_ctas();
+    const uint32_t rank = cluster_cta_rank();
+    const int64_t n_clusters = gridDim.x / C;
+    const int64_t cluster_id = blockIdx.x / C;
+    if (tid == 0) {
+        mbar_init(&xbar[0], 1);
+        mbar_init(&xbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_sync_all();   // every peer's barriers exist before the first message
+    // Reduction 1's slots are double-buffered by row parity: on CE-only rows nothing separates
+    // one row's reduction 1 from the next row's, and a fast peer may send its next partial while
+    // a slow warp here still reads the current ones (it cannot get two rows ahead: it needs this
+    // warp's next partial first).
+    Exchange ex1{slots[0], &xbar[0], 0u}, ex2x{slots[2], &xbar[1], 0u};
+    uint32_t row_par = 0;
+
+    const float T = a.temperature;
+    const float inv_t = 1.0f / T;
+    const bool round_tempered = (a.round_flags & LICV_ROUND_TEMPERED) && DT != LICV_F32 && T != 1.0f;
+    const int64_t n_kl = a.counts ? (int64_t)a.counts[0] : a.n_kl;
+    const int64_t n_ce = a.counts ? (int64_t)a.counts[1] : a.n_ce;
+    const bool use_kl = !a.only_hard_loss;
+    const bool use_ce = a.ce_label != nullptr;
+    const float kl_w = use_kl ? a.grad_scale * T / (float)n_kl : 0.f;
+    const float ce_w = use_ce ? a.grad_scale * (a.only_hard_loss ? 1.0f : a.hard_loss_weight) /
+                                    (float)n_ce
+                              : 0.f;
+    const float eps = a.kl_eps;
+    float* row_kl = a.row_loss;
+    float* row_ce = a.row_loss + a.n_rows;
+    const int V = a.vocab;
+
+    // A row is described by (r, tr, lab): teacher row (-1 = no KL) and label (kLabNone = no CE);
+    // everything else is recomputed where it is needed instead of being carried in registers.
+    auto fetch_tr = [&](int64_t r) -> int {
+        if (!use_kl || r >= a.n_rows) return -1;
+        return a.kl_tea_row ? a.kl_tea_row[r] : (int)r;
+    };
+    auto fetch_lab = [&](int64_t r) -> int {
+        if (!use_ce || r >= a.n_rows) return kLabNone;
+        const int64_t l = a.ce_label[r];
+        return (l < -100 || l > 0x7fffffff) ? kLabBad : (int)l;
+    };
+    auto x_row = [&](int64_t r) { return static_cast<const char*>(a.stu) + (size_t)r * a.stu_stride * EB; };
+    auto t_row = [&](int tr) { return static_cast<const char*>(a.tea) + (size_t)tr * a.tea_stride * EB; };
+    auto g_row = [&](int64_t r) { return static_cast<char*>(a.dstu) + (size_t)r * a.stu_stride * EB; };
+    auto phase16 = [](const void* p) { return (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u); };
+    // first element of this thread's first vector of row r (the others follow every kStep)
+    auto j_first = [&](const char* xr) -> int {
+        return (((int)rank * NV) * kT + tid) * EPV - (int)(phase16(xr) / EB);
+    };
+    // every one of this thread's vectors lies wholly inside the row (all but the threads at the
+    // row's two ends): no per-vector range checks
+    auto all_full = [&](int j0) -> bool { return j0 >= 0 && j0 + (NV - 1) * kStep + EPV <= V; };
+
+    uint4 xs[NV], xt[NV];
+    auto load_raw = [&](int64_t r, int tr, int lab) {
+        if (tr < 0 && lab == kLabNone) return;
+        const char* xr = x_row(r);
+        const int j0 = j_first(xr);
+        const bool full = all_full(j0);
+        if (full) {
+            const char* px = xr + (int64_t)j0 * EB;
+#pragma unroll
+            for (int k = 0; k < NV; ++k)
+                xs[k] = ld_stream(reinterpret_cast<const uint4*>(px + (size_t)k * kStep * EB));
+        } else {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) xs[k] = load_row_vec<DT>(xr, j0 + k * kStep, V, 16);
+        }
+        if (tr >= 0) {
+            const char* tp = t_row(tr);
+            const uint32_t dph = (phase16(tp) - phase16(xr)) & 15u;
+            if (full && dph == 0) {
+                const char* pt = tp + (int64_t)j0 * EB;
+#pragma unroll
+                for (int k = 0; k < NV; ++k)
+                    xt[k] = ld_stream(reinterpret_cast<const uint4*>(pt + (size_t)k * kStep * EB));
+            } else {
+                const int align = dph == 0 ? 16 : (int)(dph & (0u - dph));   // 8, 4 or 2
+#pragma unroll
+                for (int k = 0; k < NV; ++k) xt[k] = load_row_vec<DT>(tp, j0 + k * kStep, V, align);
+            }
+        }
+    };
+    auto store_grad = [&](char* gr_row, bool g_vec, int j0, bool full, int k, const float* gr) {
+        if (full && g_vec)
+            st_vec(reinterpret_cast<uint4*>(gr_row + ((int64_t)j0 + (int64_t)k * kStep) * EB), pack<DT>(gr));
+        else
+            store_row_vec<DT>(gr_row, j0 + k * kStep, V, g_vec, gr);
+    };
+    // the thread's integer maximum of u = logit * c (>= every u, so every e below is <= 1)
+    auto thread_max = [&](const uint4 (&raw)[NV], float it_row, bool rnd) -> int {
+        RawMax<DT> mx;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) mx.add(raw[k]);
+        float m = mx.get() * it_row;                           // monotone: max, then temper
+        if (rnd) m = Fmt<DT>::round(m);
+        m = fminf(fmaxf(ceilf(m * kLog2e), -1.0e6f), 1.0e6f);  // -inf (empty) -> -1e6
+        return (int)m;
+    };
+    // sweep B for one row: e = 2^(u - m) into the cache, returns the thread's sum
+    auto sweep_b = [&](const uint4 (&raw)[NV], float m, float c_row, float it_row, bool rnd,
+                       float4* dst) -> float {
+        float z = 0.f;
+        if (rnd) {   // the tempered logit is stored in the logits' dtype (icv_module.py:122-123)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                float x[EPV];
+                unpack<DT>(raw[k], x);
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) {
+                    x[e] = ex2(fmaf(Fmt<DT>::round(x[e] * it_row), c_row, -m));
+                    z += x[e];
+                }
+#pragma unroll
+                for (int h = 0; h < Q; ++h)
+                    dst[(k * Q + h) * kT + tid] =
+                        make_float4(x[4 * h], x[4 * h + 1], x[4 * h + 2], x[4 * h + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                float x[EPV];
+                unpack<DT>(raw[k], x);
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) {
+                    x[e] = ex2(fmaf(x[e], c_row, -m));
+                    z += x[e];
+                }
+#pragma unroll
+                for (int h = 0; h < Q; ++h)
+                    dst[(k * Q + h) * kT + tid] =
+                        make_float4(x[4 * h], x[4 * h + 1], x[4 * h + 2], x[4 * h + 3]);
+            }
+        }
+        return z;
+    };
+
+    // software pipeline over this cluster's rows: the raw logits of row `r` are in registers,
+    // (tr_n, lab_n) describe the row after it
+    int64_t r = cluster_id;
+    int tr = fetch_tr(r), lab = fetch_lab(r);
+    if (r < a.n_rows) load_raw(r, tr, lab);
+    int tr_n = fetch_tr(r + n_clusters), lab_n = fetch_lab(r + n_clusters);
+#ifdef LICV_TRACE
+    int trace_row = -1;
+#endif
+    while (r < a.n_rows) {
+        const int64_t rn = r + n_clusters;
+#ifdef LICV_TRACE
+        ++trace_row;
+#endif
+        LICV_TP(0);
+        const bool has_kl = tr >= 0, has_ce = lab != kLabNone;
+        if (!has_kl && !has_ce) {
+            // neither loss touches this row: its gradient is zero
+            if (a.dstu) {
+                float z[EPV];
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) z[e] = 0.f;
+                const char* xr = x_row(r);
+                char* gp = g_row(r);
+                const int j0 = j_first(xr);
+                const bool full = all_full(j0), g_vec = phase16(gp) == phase16(xr);
+#pragma unroll
+                for (int k = 0; k < NV; ++k) store_grad(gp, g_vec, j0, full, k, z);
+            }
+            if (rank == 0 && tid == 0) { row_kl[r] = 0.f; row_ce[r] = 0.f; }
+        } else {
+            // KL rows work on the tempered logits, CE-only rows on the raw ones
+            const float it_row = has_kl ? inv_t : 1.0f;
+            const bool rnd_row = has_kl && round_tempered;
+            const float c_row = rnd_row ? kLog2e : kLog2e * it_row;
+            // the label logit, before the gradient may overwrite the row in place
+            const bool lab_ok = has_ce && lab >= 0 && lab < V;
+            float x_lab = 0.f;
+            if (rank == 0 && tid == 0 && lab_ok) x_lab = load_elem<DT>(x_row(r), lab);
+
+            // ---- sweep B: exponentials relative to the thread's own maxima -> cache -----------
+            MZ2 mine{kNoMaxI, 0.f, kNoMaxI, 0.f};
+            mine.ms = thread_max(xs, it_row, rnd_row);
+            mine.zs = sweep_b(xs, (float)mine.ms, c_row, it_row, rnd_row, cs);
+            if (has_kl) {
+                mine.mt = thread_max(xt, it_row, rnd_row);
+                mine.zt = sweep_b(xt, (float)mine.mt, c_row, it_row, rnd_row, ct);
+            }
+            LICV_TP(1);
+            // ---- the raw registers are free: request the next row now; it lands during the
+            //      reductions and sweeps below.  Then look up the row after that. ---------------
+            if (rn < a.n_rows) load_raw(rn, tr_n, lab_n);
+            const int tr_nn = fetch_tr(rn + n_clusters), lab_nn = fetch_lab(rn + n_clusters);
+
+            // ---- reduction 1: maxima and partition sums of both rows ---------------------------
+            ex1.slots = slots[row_par];
+            row_par ^= 1u;
+            {
+                const MZ2 w = mz_warp(mine);
+                exchange_send(ex1, make_float4(__int_as_float(w.ms), w.zs, __int_as_float(w.mt), w.zt),
+                              rank, C);
+            }
+            LICV_TP(2);
+            const MZ2 tot = exchange_recv_mz(ex1, C);
+            LICV_TP(3);
+            const float fs = pow2i(mine.ms - tot.ms) * rcp(tot.zs);      // q = e_s * fs
+
+            // ---- sweep C: KL terms and W_n ------------------------------------------------------
+            float W = 0.f, kl_row = 0.f;
+            if (has_kl) {
+                const float ft = pow2i(mine.mt - tot.mt) * rcp(tot.zt);  // p = e_t * ft
+                float klp = 0.f, wp = 0.f;
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+#pragma unroll
+                    for (int h = 0; h < Q; ++h) {
+                        const float4 es = cs[(k * Q + h) * kT + tid];
+                        const float4 et = ct[(k * Q + h) * kT + tid];
+                        const float ea[4] = {es.x, es.y, es.z, es.w};
+                        const float eb[4] = {et.x, et.y, et.z, et.w};
+                        float wk[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float q = ea[e] * fs;
+                            const float p = eb[e] * ft;
+                            const float rq = rcp(q + eps);
+                            // ln(p+eps) - ln(q+eps) = ln((p+eps)/(q+eps))
+                            klp = fmaf(p, lg2((p + eps) * rq), klp);
+                            const float w = p * q * rq;
+                            wp += w;
+                            wk[e] = w * kl_w;
+                        }
+                        if (a.dstu) ct[(k * Q + h) * kT + tid] = make_float4(wk[0], wk[1], wk[2], wk[3]);
+                    }
+                }
+                LICV_TP(4);
+                // ---- reduction 2: KL_n and W_n --------------------------------------------------
+                exchange_send(ex2x, make_float4(warp_sum(klp), warp_sum(wp), 0.f, 0.f), rank, C);
+                const float2 r2 = exchange_recv_sum(ex2x, C);
+                LICV_TP(5);
+                kl_row = r2.x * kLn2;
+                W = r2.y;
+            }
+
+            // ---- sweep D: gradient ----------------------------------------------------------------
+            if (a.dstu) {
+                const float ce_on = has_ce ? ce_w : 0.f;
+                const float A = fs * fmaf(kl_w, W, ce_on);    // has_kl false: W = 0 -> fs * ce_w
+                const char* xr = x_row(r);
+                char* gp = g_row(r);
+                const int j0 = j_first(xr);
+                const bool full = all_full(j0), g_vec = phase16(gp) == phase16(xr);
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                    float gr[EPV];
+#pragma unroll
+                    for (int h = 0; h < Q; ++h) {
+                        const float4 es = cs[(k * Q + h) * kT + tid];
+                        float4 wk = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (has_kl) wk = ct[(k * Q + h) * kT + tid];
+                        gr[4 * h] = fmaf(es.x, A, -wk.x);
+                        gr[4 * h + 1] = fmaf(es.y, A, -wk.y);
+                        gr[4 * h + 2] = fmaf(es.z, A, -wk.z);
+                        gr[4 * h + 3] = fmaf(es.w, A, -wk.w);
+                    }
+                    if (has_ce) {
+                        const unsigned rel = (unsigned)(lab - (j0 + k * kStep));
+                        if (rel < (unsigned)EPV && lab >= 0) {
+#pragma unroll
+                            for (int e = 0; e < EPV; ++e)
+                                if (e == (int)rel) gr[e] -= ce_on;
+                        }
+                    }
+                    store_grad(gp, g_vec, j0, full, k, gr);
+                }
+            }
+            LICV_TP(6);
+            if (rank == 0 && tid == 0) {
+                row_kl[r] = kl_row;
+                float ce = 0.f;
+                if (has_ce)  // an out-of-range label is an error in torch; poison the loss instead
+                    ce = lab_ok ? ((float)tot.ms + lg2(tot.zs)) * kLn2 - x_lab : __int_as_float(0x7fc00000);
+                row_ce[r] = ce;
+            }
+            r = rn;
+            tr = tr_n; lab = lab_n;
+            tr_n = tr_nn; lab_n = lab_nn;
+            continue;
+        }
+        // (row in neither loss) advance: nothing was prefetched for the next row yet
+        r = rn;
+        tr = tr_n; lab = lab_n;
+        if (r < a.n_rows) load_raw(r, tr, lab);
+        tr_n = fetch_tr(r + n_clusters); lab_n = fetch_lab(r + n_clusters);
+    }
+
+    cluster_sync_all();   // no CTA leaves while a peer may still send to it
+    // ---- the last CTA to finish reduces the per-row losses (fixed order: deterministic) --------
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned done_ctas = atomicAdd(a.counter, 1u);
+        s_last = (done_ctas == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        float tk = 0.f, tc = 0.f;
+        for (int64_t i = tid; i < a.n_rows; i += kT) {
+            tk += __ldcg(row_kl + i);
+            tc += __ldcg(row_ce + i);
+        }
+        tk = warp_sum(tk);
+        tc = warp_sum(tc);
+        if ((tid & 31) == 0) { s_tot[tid >> 5] = tk; s_tot[kWarps + (tid >> 5)] = tc; }
+        __syncthreads();
+        if (tid == 0) {
+            tk = 0.f; tc = 0.f;
+            for (int w = 0; w < kWarps; ++w) { tk += s_tot[w]; tc += s_tot[kWarps + w]; }
+            const float kl = use_kl ? tk * T * T / (float)n_kl : 0.f;
+            const float ce = use_ce ? tc / (float)n_ce : 0.f;
+            a.out_losses[0] = kl;
+            a.out_losses[1] = ce;
+            a.out_losses[2] = a.only_hard_loss ? ce : (use_ce ? fmaf(a.hard_loss_weight, ce, kl) : kl);
+            *a.counter = 0u;  // leave the workspace ready for the next call
+        }
+    }
+}
+
+inline int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
+}
+
+template <int DT, int NV>
+int launch_cluster(const KdArgs& a, int C, cudaStream_t st) {
+    auto kern = kd_loss_cluster_kernel<DT, NV>;
+    constexpr size_t smem = (size_t)2 * NV * Fmt<DT>::kPerVec * kT * sizeof(float);
+    static bool raised = false;
+    if (!raised && smem > 48 * 1024) {
+        const cudaError_t e =
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (!raised && C > 8) return LICV_ERR_BAD_ARGUMENT;
+    raised = true;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;   // st.async / mapa are cluster instructions: C = 1 is launched as a cluster too
+    // clusters resident at once (per instantiation and cluster size; one process drives one GPU)
+    static int64_t cap[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (cap[C] == 0) {
+        int n = 0;
+        cfg.gridDim = dim3(C * device_info().sm_count);
+        if (C > 1 && cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) {
+            cap[C] = n;
+        } else {
+            cudaGetLastError();
+            int per_sm = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kT, smem) != cudaSuccess ||
+                per_sm < 1)
+                per_sm = 1;
+            cap[C] = (int64_t)per_sm * device_info().sm_count / C;
+            if (cap[C] < 1) cap[C] = 1;
+        }
+    }
+    int64_t clusters = a.n_rows < cap[C] ? a.n_rows : cap[C];
+    if (clusters < 1) clusters = 1;   // no rows: the finalising CTA still reports mean-of-empty
+    cfg.gridDim = dim3((unsigned)(clusters * C));
+    return (int)cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+template <int DT>
+int dispatch_nv(const KdArgs& a, int C, int NV, cudaStream_t st) {
+    switch (NV) {
+        case 1: return launch_cluster<DT, 1>(a, C, st);
+        case 2: return launch_cluster<DT, 2>(a, C, st);
+        case 4: return launch_cluster<DT, 4>(a, C, st);
+        default: return launch_cluster<DT, 8>(a, C, st);
+    }
+}
+
+}  // namespace
+
+#ifdef LICV_TRACE
+extern "C" int licv_debug_read_trace(long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g_trace, sizeof(long long) * n);
+}
+#endif
+
+bool kd_cluster_plan(int vocab, int dtype, float temperature, bool kl_and_ce, int* C, int* NV) {
+    static const int off = env_int("LICV_KD_NO_CLUSTER", 0);
+    if (off) return false;
+    // a KL + CE row at T != 1 needs a third exponential stream (CE works on the raw logits):
+    // left to the generic kernel
+    if (kl_and_ce && temperature != 1.0f) return false;
+    const int epv = dtype == LICV_F32 ? 4 : 8;
+    const int64_t need = ((int64_t)vocab + epv - 1) / epv + 1;   // + 1: a row may straddle
+    for (int nv = 1; nv <= 4; nv *= 2)
+        if ((int64_t)nv * kT >= need) { *C = 1; *NV = nv; return true; }
+    for (int c = 2; c <= 8; c *= 2)
+        if ((int64_t)c * 4 * kT >= need) { *C = c; *NV = 4; return true; }
+    if ((int64_t)8 * 8 * kT >= need) { *C = 8; *NV = 8; return true; }
+    return false;
+}
+
+int launch_kd_cluster(const KdArgs& a, int dtype, int C, int NV, cudaStream_t st) {
+    switch (dtype) {
+        case LICV_F32: return dispatch_nv<LICV_F32>(a, C, NV, st);
+        case LICV_BF16: return dispatch_nv<LICV_BF16>(a, C, NV, st);
+        default: return dispatch_nv<LICV_F16>(a, C, NV, st);
+    }
+}
+
+}  // namespace licv

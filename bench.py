@@ -312,8 +312,8 @@ def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return 0
-    steps = max(1, min(args.steps, 20))
-    warm = max(1, min(args.warmup, 3))
+    steps = max(1, args.steps)      # one step = 8 samples = ~50 ms of host work: K steps as asked
+    warm = max(0, args.warmup)
     sec, cores = cpu_reference_steps(steps, warm)
     val = CFG["batch_per_gpu"] / sec
     line = {
@@ -535,21 +535,63 @@ def main():
                                                   hp.out[l].data_ptr(), n_tok, d, hp.code, hp.code,
                                                   hp.flags, st)
 
-        time_kernel_launches([bwd_launch(l) for l in range(L)], stream)      # warm
-        tb = time_kernel_launches([bwd_launch(l) for l in reversed(range(L))], stream)
-        tf = time_kernel_launches([fwd_launch(l) for l in range(L)], stream)
-        t_bwd = sum(tb) / len(tb)
+        def kd_launch():
+            V = CFG["vocab"]
+            return hp.lib.licv_kd_loss_fwd_bwd(
+                batch["stu"].data_ptr(), hp.dstu.data_ptr(), batch["tea"].data_ptr(),
+                hp.kl_tea_row.data_ptr(), hp.ce_label.data_ptr(), hp.counts.data_ptr(), 0, 0,
+                CFG["temperature"], CFG["kl_eps"], CFG["hard_loss_weight"], 0, 1.0,
+                hp.losses.data_ptr(), hp.ws.data_ptr(), n_tok, V, V, V, hp.code,
+                hp.abi.ROUND_TEMPERED, st)
+
+        def graph_time(launches, reps=20):
+            """Seconds per launch: the launches captured as one CUDA graph (no host gaps between
+            them), CUDA events on the launching stream around `reps` replays."""
+            for fn in launches:
+                fn()
+            stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for fn in launches:
+                    fn()
+            for _ in range(3):
+                g.replay()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                g.replay()
+            b.record(stream)
+            stream.synchronize()
+            return a.elapsed_time(b) * 1e-3 / (reps * len(launches))
+
+        t_bwd = graph_time([bwd_launch(l) for l in reversed(range(L))])
+        t_fwd = graph_time([fwd_launch(l) for l in range(L)])
+        t_kd = graph_time([kd_launch])
         bytes_bwd = 3 * es * n_tok * d
+        n_kl_rows = CFG["batch_per_gpu"] * CFG["kl_rows_per_sample"]
+        n_ce_rows = CFG["batch_per_gpu"] * (CFG["student_tokens"] - 1)
+        n_dead = n_tok - n_ce_rows
+        bytes_kd = es * CFG["vocab"] * (3 * n_kl_rows + 2 * (n_ce_rows - n_kl_rows) + n_dead)
         roofline = {"bound": "hbm", "kernel": "licv_inject_bwd",
                     "achieved": bytes_bwd / t_bwd / 1e9, "peak": peak, "unit": "GB/s",
                     "frac": bytes_bwd / t_bwd / 1e9 / peak, "traffic": None,
                     "peak_source": peak_src, "bytes_per_launch": bytes_bwd,
                     "us_per_launch": t_bwd * 1e6, "launches_per_step": L,
                     "share_of_step": L * t_bwd / (ms_per_step * 1e-3),
-                    "how": "CUDA events around each of the 32 launches on the launching stream, "
-                           "eager pass right after the timed region (the timed region itself is "
-                           "one CUDA graph per step); 256 tokens per launch = 6 MB: latency-bound",
-                    "fwd_us_per_launch": sum(tf) / len(tf) * 1e6}
+                    "how": "the step's 32 launches of the kernel captured as one CUDA graph "
+                           "(distinct h/g/dh buffers per layer, 200 MB > L2 between reuses), "
+                           "CUDA events on the launching stream around 20 replays, right after "
+                           "the timed region; 256 tokens per launch = 6 MB: latency-bound, see "
+                           "roofline_bw for the same kernel at bandwidth-bound sizes",
+                    "other_kernels": [
+                        {"kernel": "licv_inject_fwd", "us_per_launch": t_fwd * 1e6,
+                         "launches_per_step": L, "bytes_per_launch": 2 * es * n_tok * d,
+                         "achieved": 2 * es * n_tok * d / t_fwd / 1e9,
+                         "share_of_step": L * t_fwd / (ms_per_step * 1e-3)},
+                        {"kernel": "licv_kd_loss_fwd_bwd", "us_per_launch": t_kd * 1e6,
+                         "launches_per_step": 1, "bytes_per_launch": bytes_kd,
+                         "achieved": bytes_kd / t_kd / 1e9,
+                         "share_of_step": t_kd / (ms_per_step * 1e-3)}]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

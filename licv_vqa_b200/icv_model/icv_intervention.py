@@ -22,6 +22,7 @@ What is different underneath:
 from __future__ import annotations
 
 import re
+import weakref
 from typing import List, Optional, Union
 
 import torch
@@ -88,6 +89,10 @@ class LearnableICVInterventionLMM(nn.Module):
 
     # ------------------------------------------------------------------ hooks (installed once)
     def _install_hooks(self):
+        # Hooks are persistent, so a tower must have ONE owner: wrapping the same lmm again (a new
+        # module over a shared frozen tower) retires the previous wrapper's hooks, which would
+        # otherwise keep injecting that wrapper's last ICV (the reference's hooks die with its
+        # `with` block, icv_intervention.py:112-113).
         named = dict(self.lmm.named_modules())
         for name in self.intervention_layer_names:
             if name not in named:
@@ -96,6 +101,13 @@ class LearnableICVInterventionLMM(nn.Module):
             # (icv_intervention.py:63), KeyError included when that is not a hooked layer id
             layer_idx = int(re.findall(r"\d+", name)[0])
             icv_index = self.layer_to_icv_index[layer_idx]
+            # ownership is recorded on the hooked submodule itself (the same tower may sit behind
+            # different interface objects)
+            previous = named[name].__dict__.get("_licv_hook_owner")
+            previous = previous() if previous is not None else None
+            if previous is not None and previous is not self:
+                previous.remove_hooks()
+            named[name].__dict__["_licv_hook_owner"] = weakref.ref(self)
             self._hook_handles.append(
                 named[name].register_forward_hook(self._make_hook(icv_index)))
 
@@ -120,9 +132,17 @@ class LearnableICVInterventionLMM(nn.Module):
                           active.sink[icv_index])
 
     def remove_hooks(self):
+        """Detach from the tower (the wrapper then behaves as if intervention were disabled)."""
         for h in self._hook_handles:
             h.remove()
         self._hook_handles = []
+        self._active = None
+
+    def __del__(self):
+        try:
+            self.remove_hooks()
+        except Exception:  # interpreter shutdown
+            pass
 
     # ------------------------------------------------------------------ reference API
     @property

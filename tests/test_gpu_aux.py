@@ -1,0 +1,226 @@
+"""GPU parity of the small kernels around the two hot ones and of the host-buffer entry points:
+encoder product (a1+a2), get_mask (a6), row pairing / CE labels (a6+a7+a9), the fused clip+AdamW
+step (f2), the data-parallel optimizer at world size 1, licv_*_host vs the device entry points."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import licv_oracle as O
+from tests.util import EPS, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from licv_vqa_b200 import ops as _ops
+    return _ops
+
+
+def host(t):
+    return t.detach().float().cpu().numpy().astype(np.float64)
+
+
+ENC = load_golden("encoder_cases.npz")
+
+
+@pytest.mark.parametrize("name", [str(n) for n in ENC["names"]])
+def test_encoder_product_matches_reference_golden(ops, name):
+    L, d, learn, sig = [int(x) for x in ENC[f"{name}/cfg"]]
+    from licv_vqa_b200 import GlobalICVEncoder
+    enc = GlobalICVEncoder(d, L, alpha_learnable=bool(learn), alpha_init_value=0.0,
+                           use_sigmoid=bool(sig)).cuda()
+    assert sorted(enc.state_dict().keys()) == ["alpha", "icv"]
+    with torch.no_grad():
+        enc.alpha.copy_(torch.tensor(ENC[f"{name}/alpha_raw"]))
+        enc.icv.copy_(torch.tensor(ENC[f"{name}/vec"]))
+    out = enc()
+    assert out.in_context_feature is None
+    assert rel_err(host(out.alpha), ENC[f"{name}/alpha_eff"]) < 1e-6
+    icv = enc.scaled_icv()
+    assert icv.shape == (1, L, d)
+    assert rel_err(host(icv), ENC[f"{name}/icv"]) < 1e-6
+    icv.backward(torch.tensor(ENC[f"{name}/g"]).cuda())
+    assert rel_err(host(enc.icv.grad), ENC[f"{name}/dvec"]) < 1e-6
+    if learn:
+        assert rel_err(host(enc.alpha.grad), ENC[f"{name}/dalpha"]) < 1e-5
+    else:
+        assert enc.alpha.grad is None
+
+
+MASK = load_golden("mask_cases.npz")
+
+
+@pytest.mark.parametrize("name", [str(n) for n in MASK["names"]])
+def test_get_mask_matches_reference_golden(ops, name):
+    ids = torch.tensor(MASK[f"{name}/ids"]).cuda()
+    lens = torch.tensor(MASK[f"{name}/len"]).cuda()
+    m = ops.get_mask(ids, lens, int(MASK[f"{name}/pad"]))
+    assert m.dtype == torch.bool
+    assert np.array_equal(m.cpu().numpy(), MASK[f"{name}/mask"])     # bit-exact
+
+
+@pytest.mark.parametrize("variant", ["idefics", "idefics2", "causal_lm"])
+@pytest.mark.parametrize("B,Tq,Tc", [(4, 12, 40), (8, 32, 896), (1, 5, 3), (3, 700, 1300)])
+def test_prepare_rows_vs_oracle(ops, variant, B, Tq, Tc):
+    rng = np.random.default_rng(B * 1000 + Tq)
+    qx = rng.integers(1, Tq, size=B)
+    s_ids = rng.integers(3, 100, size=(B, Tq))
+    s_att = np.ones((B, Tq), np.int64)
+    for b in range(0, B, 2):                         # right padding on some rows
+        npad = int(rng.integers(0, max(Tq // 3, 1)))
+        if npad:
+            s_ids[b, Tq - npad:] = 0
+            s_att[b, Tq - npad:] = 0
+    img = 32001 if variant == "idefics2" else -1
+    if variant == "idefics2":
+        s_ids[:, 2:4] = img
+    ctx = rng.integers(3, 100, size=(B, Tc))
+    t_ids = np.concatenate([ctx, s_ids[:, 1:]], axis=1)      # the collator's contract
+    icl = Tc + qx - 1
+    s_mask = O.get_mask(s_ids, qx, 0)
+    t_mask = O.get_mask(t_ids, icl, 0)
+    want_ktr = O.pair_rows(s_mask, t_mask)
+    want_lab = O.ce_labels(s_ids, s_att, variant, img if img >= 0 else None).reshape(-1)
+    ktr, lab, counts = ops.kd_prepare_rows(
+        torch.tensor(s_ids).cuda(), torch.tensor(qx).cuda(), torch.tensor(t_ids).cuda(),
+        torch.tensor(icl).cuda(), 0, torch.tensor(s_att).cuda(), variant, img)
+    assert np.array_equal(ktr.cpu().numpy(), want_ktr)                  # bit-exact
+    assert np.array_equal(lab.cpu().numpy(), want_lab)
+    c = counts.cpu().numpy()
+    assert c[0] == (want_ktr >= 0).sum() and c[1] == (want_lab != -100).sum() and c[2] == c[0]
+    # no CE wanted: labels are not produced
+    ktr2, lab2, _ = ops.kd_prepare_rows(
+        torch.tensor(s_ids).cuda(), torch.tensor(qx).cuda(), torch.tensor(t_ids).cuda(),
+        torch.tensor(icl).cuda(), 0, None, variant, img, want_ce=False)
+    assert lab2 is None and np.array_equal(ktr2.cpu().numpy(), want_ktr)
+
+
+def test_prepare_rows_mismatched_masks_reports_counts(ops):
+    """The reference raises a shape error when the two masks select different row counts
+    (icv_module.py:126-131); the kernel reports both counts and the host side raises."""
+    s_ids = torch.randint(3, 50, (2, 6)).cuda()
+    t_ids = torch.randint(3, 50, (2, 9)).cuda()
+    _, _, counts = ops.kd_prepare_rows(s_ids, torch.tensor([2, 2]).cuda(), t_ids,
+                                       torch.tensor([2, 2]).cuda(), 0)
+    c = counts.cpu().numpy()
+    assert c[0] == 8 and c[2] == 14
+
+
+@pytest.mark.parametrize("n_vec,n_alpha,clip", [(32 * 4096, 32, 1.0), (1000, 7, 0.0), (64, 0, 0.05)])
+def test_adamw_step_vs_oracle(ops, n_vec, n_alpha, clip):
+    rng = np.random.default_rng(n_vec)
+    n = n_vec + n_alpha
+    p = rng.normal(size=n)
+    m = np.zeros(n)
+    v = np.zeros(n)
+    dp = torch.tensor(p, dtype=torch.float32).cuda()
+    dm = torch.zeros(n, device="cuda")
+    dv = torch.zeros(n, device="cuda")
+    norm = torch.zeros(1, device="cuda")
+    lr = np.concatenate([np.full(n_vec, 1e-3), np.full(n_alpha, 1e-1)])
+    world = 4.0
+    for step in range(1, 6):
+        g = rng.normal(size=n) * (10.0 if step == 2 else 0.3)
+        dg = torch.tensor(g, dtype=torch.float32).cuda()
+        gg = g / world                                      # grad_prescale = 1 / world
+        coef, tot = (1.0, np.linalg.norm(gg)) if clip <= 0 else O.clip_coef([gg], clip)
+        p, m, v = O.adamw_step(p, gg * coef, m, v, step, lr)
+        ops.adamw_step(dp, dg, dm, dv, n_vec, n_alpha, 1e-3, 1e-1, step, grad_prescale=1 / world,
+                       max_grad_norm=clip, norm_out=norm)
+        assert rel_err(host(norm), [tot]) < 1e-5
+        assert rel_err(host(dp), p) < 2e-6
+        # fp32 state: the clip coefficient comes from an fp32 sum of 131k squares, v sees it squared
+        assert rel_err(host(dm), m) < 1e-5 and rel_err(host(dv), v) < 5e-5
+
+
+def test_dp_optimizer_world1_matches_torch_adamw(ops):
+    """ICVDataParallelOptimizer (flat views + fused kernel) against torch.optim.AdamW with the
+    reference's two parameter groups, clip 1.0 and cosine warm-up (icv_module.py:171-209)."""
+    from transformers import get_cosine_schedule_with_warmup
+
+    from licv_vqa_b200 import GlobalICVEncoder
+    from licv_vqa_b200.dp import ICVDataParallelOptimizer
+    L, d, total = 4, 256, 20
+    torch.manual_seed(426)
+    enc = GlobalICVEncoder(d, L, alpha_init_value=0.1).cuda()
+    ref = GlobalICVEncoder(d, L, alpha_init_value=0.1).cuda()
+    ref.load_state_dict(enc.state_dict())
+    cfg = dict(icv_lr=1e-3, alpha_lr=1e-2, weight_decay=1e-3, warm_steps=0.1)
+    opt = ICVDataParallelOptimizer(enc, cfg, total_steps=total)
+    topt = torch.optim.AdamW([{"params": ref.alpha, "lr": 1e-2}, {"params": ref.icv}], lr=1e-3,
+                             weight_decay=1e-3)
+    sched = get_cosine_schedule_with_warmup(topt, num_warmup_steps=0.1 * total,
+                                            num_training_steps=total)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for step in range(8):
+        x = torch.randn(1, L, d, device="cuda", generator=gen) * (30.0 if step == 3 else 1.0)
+        for e in (enc, ref):
+            loss = ((e.scaled_icv() if e is enc else e.alpha.unsqueeze(-1) * e.icv) - x).pow(2).mean()
+            loss.backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+        topt.step()
+        sched.step()
+        topt.zero_grad()
+        logs = opt.step({"loss": loss.detach(), "kl_loss": loss.detach()})
+        assert float(logs["loss"]) == pytest.approx(float(loss), rel=1e-6)
+        assert rel_err(host(enc.icv), host(ref.icv)) < 5e-6
+        assert rel_err(host(enc.alpha), host(ref.alpha)) < 5e-6
+        assert enc.icv.grad.data_ptr() == opt.state.grad.data_ptr() and not enc.icv.grad.any()
+
+
+def test_host_entry_points_match_device_entry_points(ops):
+    """licv_*_host (pinned host buffers in, pinned host buffers out) == the device calls."""
+    from licv_vqa_b200 import _abi
+    lib = _abi.load()
+    rng = np.random.default_rng(11)
+    n_tok, d, V, R, Rt = 37, 4096, 32002, 9, 5
+    dt, code = torch.bfloat16, _abi.BF16
+    h = (torch.tensor(rng.normal(size=(n_tok, d)), dtype=torch.float32) * 4).to(dt).pin_memory()
+    g = torch.tensor(rng.normal(size=(n_tok, d)), dtype=torch.float32).to(dt).pin_memory()
+    s = torch.tensor(rng.normal(size=d), dtype=torch.float32).pin_memory()
+    out_h = torch.empty_like(h).pin_memory()
+    dh_h = torch.empty_like(h).pin_memory()
+    ds_h = torch.empty(d).pin_memory()
+    sess = C.c_void_p()
+    _abi.check(lib.licv_host_session_create(C.byref(sess), 64 << 20, 3), "create")
+    try:
+        _abi.check(lib.licv_inject_fwd_host(sess, h.data_ptr(), s.data_ptr(), out_h.data_ptr(), n_tok,
+                                            d, code, code, 0), "fwd_host")
+        _abi.check(lib.licv_inject_bwd_host(sess, h.data_ptr(), g.data_ptr(), s.data_ptr(),
+                                            dh_h.data_ptr(), ds_h.data_ptr(), n_tok, d, code, code, 0),
+                   "bwd_host")
+        stu = (torch.tensor(rng.normal(size=(R, V)), dtype=torch.float32) * 3).to(dt).pin_memory()
+        tea = (torch.tensor(rng.normal(size=(Rt, V)), dtype=torch.float32) * 3).to(dt).pin_memory()
+        ktr = torch.tensor([0, -1, 1, 2, -1, -1, 3, 4, -1], dtype=torch.int32).pin_memory()
+        lab = torch.tensor(rng.integers(0, V, size=R)).pin_memory()
+        lab[1] = -100
+        dstu_h = torch.empty_like(stu).pin_memory()
+        loss_h = torch.zeros(3).pin_memory()
+        _abi.check(lib.licv_kd_loss_fwd_bwd_host(sess, stu.data_ptr(), dstu_h.data_ptr(), tea.data_ptr(),
+                                                 ktr.data_ptr(), lab.data_ptr(), 5, 8, 1.0, 1e-6, 0.5, 0,
+                                                 1.0, loss_h.data_ptr(), R, Rt, V, code, 16), "kd_host")
+        _abi.check(lib.licv_host_sync(sess), "sync")
+    finally:
+        lib.licv_host_session_destroy(sess)
+    sd = s.cuda()
+    out_d = ops.inject_forward(h.cuda(), sd, dt, 0)
+    ds_d = torch.zeros(d, device="cuda")
+    dh_d = ops.inject_backward(h.cuda(), g.cuda(), sd, ds_d, True, 0)
+    assert torch.equal(out_h.cuda(), out_d) and torch.equal(dh_h.cuda(), dh_d)
+    assert rel_err(host(ds_h), host(ds_d)) < 1e-6          # atomics: order may differ
+    losses, dstu_d = ops.kd_loss_raw(stu.cuda(), tea.cuda(), ktr.cuda(), lab.cuda(), None, 5, 8, 1.0,
+                                     1e-6, 0.5, in_place=False)
+    assert torch.equal(dstu_h.cuda(), dstu_d)
+    assert np.allclose(host(loss_h), host(losses), rtol=1e-6)
+    want = O.kd_loss_rows(host(stu), host(tea), ktr.numpy(), lab.numpy(), 1.0, 1e-6, 0.5)
+    assert abs(float(loss_h[2]) - want["loss"]) <= 1e-5 * abs(want["loss"])
+
+
+def test_no_cpu_path(ops):
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.inject_forward(torch.zeros(2, 8), torch.zeros(8))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.kd_loss_raw(torch.zeros(2, 8), torch.zeros(2, 8))

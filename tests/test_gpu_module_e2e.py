@@ -1,0 +1,108 @@
+"""BASELINE configs[0] end to end on the GPU: the tiny random-init LLaMA tower (2 layers, d=512,
+V=32000) wrapped by OUR VQAICVModule / LearnableICVInterventionLMM / GlobalICVEncoder, against the
+golden losses and ICV gradients the REAL reference produced on the same weights and inputs
+(tests/golden/config1_e2e.npz, made by oracle/make_golden.py).  Tolerance: 1e-4 relative on loss
+and on the ICV gradients (north_star), fp32 tower on both sides."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+G = load_golden("config1_e2e.npz")
+
+
+def tiny_llama(seed=426, vocab=32000, hidden=512, layers=2):
+    from transformers import LlamaConfig, LlamaForCausalLM
+    torch.manual_seed(seed)
+    cfg = LlamaConfig(vocab_size=vocab, hidden_size=hidden, intermediate_size=1376,
+                      num_hidden_layers=layers, num_attention_heads=8, num_key_value_heads=8,
+                      max_position_embeddings=256, pad_token_id=0, bos_token_id=1, eos_token_id=2,
+                      tie_word_embeddings=False, attn_implementation="eager")
+    model = LlamaForCausalLM(cfg)
+    model.eval()
+    return model
+
+
+class Interface(torch.nn.Module):
+    """Duck-typed lmm_icl_interface.LMMInterface (attributes used at icv_module.py:28-30,137-146)."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+        self.tokenizer = type("Tok", (), {"pad_token_id": 0})()
+        self.input_ids_field_name = "input_ids"
+
+    @property
+    def device(self):
+        return next(self.model.parameters()).device
+
+    def forward(self, **kw):
+        return self.model(**kw)
+
+    def generate(self, **kw):
+        return self.model.generate(**kw)
+
+
+@pytest.fixture(scope="module")
+def tower():
+    model = tiny_llama()
+    chk = np.array([float(p.detach().double().abs().sum()) for p in model.parameters()])
+    if not np.allclose(chk, G["weight_checksum"], rtol=1e-12):
+        pytest.skip("this torch/transformers build initialises the tower differently from the fixture")
+    return model.cuda()
+
+
+@pytest.mark.parametrize("name", [str(n) for n in G["names"]])
+def test_module_matches_reference_end_to_end(tower, name):
+    from licv_vqa_b200 import LMMConfig, ModuleConfig, VQAICVModule
+    from licv_vqa_b200.icv_module import ICVEncoderConfig
+    sig, hlw, T = G[f"{name}/cfg"]
+    cfg = ModuleConfig(hard_loss_weight=float(hlw), init_temperature=float(T), kl_eps=1e-6,
+                       ce_variant="causal_lm",   # what the fixture's transformers computes
+                       icv_encoder=ICVEncoderConfig(use_sigmoid=bool(sig), alpha_init_value=0.1))
+    lmm = LMMConfig("tiny-llama", 2, "model.model.layers.<LAYER_NUM>", -1, 512)
+    mod = VQAICVModule(Interface(tower), cfg, lmm).cuda()
+    with torch.no_grad():
+        mod.icv_encoder.alpha.copy_(torch.tensor(G[f"{name}/alpha_raw"]))
+        mod.icv_encoder.icv.copy_(torch.tensor(G[f"{name}/vec"]))
+    dev = "cuda"
+    q = {"input_ids": torch.tensor(G["q_ids"]).to(dev), "attention_mask": torch.tensor(G["q_att"]).to(dev)}
+    t = {"input_ids": torch.tensor(G["t_ids"]).to(dev), "attention_mask": torch.tensor(G["t_att"]).to(dev)}
+    loss_dict, enc_out = mod(q, t, torch.tensor(G["query_x_length"]).to(dev),
+                             torch.tensor(G["in_context_length"]).to(dev))
+    loss_dict["loss"].backward()
+    kl, loss = float(loss_dict["kl_loss"]), float(loss_dict["loss"])
+    assert abs(kl - float(G[f"{name}/kl_loss"])) <= 1e-4 * abs(float(G[f"{name}/kl_loss"]))
+    assert abs(loss - float(G[f"{name}/loss"])) <= 1e-4 * abs(float(G[f"{name}/loss"]))
+    if hlw:
+        ce = float(loss_dict["ce_loss"])
+        assert abs(ce - float(G[f"{name}/ce_loss"])) <= 1e-4 * abs(float(G[f"{name}/ce_loss"]))
+    else:
+        assert "ce_loss" not in loss_dict
+    dv = mod.icv_encoder.icv.grad.float().cpu().numpy()
+    da = mod.icv_encoder.alpha.grad.float().cpu().numpy()
+    assert rel_err(dv, G[f"{name}/dvec"]) < 1e-4
+    assert rel_err(da, G[f"{name}/dalpha"]) < 1e-4
+    # hooks are persistent and the toggle works like the reference's
+    assert len(mod.icv_model._hook_handles) == 2
+    with pytest.raises(ValueError):
+        mod.icv_model.intervention_status = "yes"
+
+
+def test_generate_with_icv_runs_and_changes_output(tower):
+    """inference.py:309-313: model.generate(**inputs, icv=alpha.unsqueeze(-1) * vec)."""
+    from licv_vqa_b200 import LearnableICVInterventionLMM
+    name = str(G["names"][0])
+    m = LearnableICVInterventionLMM(Interface(tower), True, -1, "model.model.layers.<LAYER_NUM>", 2)
+    alpha = torch.tensor(G[f"{name}/alpha_raw"]).cuda()
+    vec = torch.tensor(G[f"{name}/vec"]).cuda() * 50
+    ids = torch.tensor(G["q_ids"][:2, :8]).cuda()
+    with torch.no_grad():
+        a = m.generate(icv=alpha.unsqueeze(-1) * vec, input_ids=ids, max_new_tokens=4, do_sample=False)
+        m.toggle_intervention(False)
+        b = m.generate(input_ids=ids, max_new_tokens=4, do_sample=False)
+    assert a.shape == b.shape == (2, 12)
+    assert not torch.equal(a, b)

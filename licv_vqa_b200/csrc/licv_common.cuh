@@ -168,6 +168,17 @@ struct DeviceInfo {
 };
 const DeviceInfo& device_info();
 
+// Upper bound on the CTAs of the next injection launches of this thread (0 = none).  The
+// host-buffer entry points set it: when the operands live in host memory the link, not the SMs,
+// is the bottleneck, and a SMALL persistent grid lets each CTA's loads of token t+1 overlap its
+// stores of token t, i.e. keeps both directions of the link busy inside one kernel.
+extern thread_local int tl_grid_cap;
+struct GridCapScope {
+    int saved;
+    explicit GridCapScope(int cap) : saved(tl_grid_cap) { tl_grid_cap = cap; }
+    ~GridCapScope() { tl_grid_cap = saved; }
+};
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace licv

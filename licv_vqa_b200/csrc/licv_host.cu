@@ -1,7 +1,18 @@
 // Host-buffer entry points: the calls a host-side plugin makes when its tensors live in host
 // memory.  A session owns n_slots (device scratch, stream) pairs; call k runs entirely on slot
-// k % n_slots, so the copy-in of one call overlaps the kernel of the previous one and the
-// copy-out of the one before.  Pinned host buffers make the copies truly asynchronous.
+// k % n_slots.
+//
+// Two data paths:
+//  * ZERO-COPY (pinned / registered host buffers, the normal case): the kernels are launched
+//    directly on the device view of the host buffers - hidden states and logits are read over
+//    PCIe by the kernel's own 128-bit loads / TMA bulk copies and results are written straight
+//    back to host memory, so both directions of the link are busy at once inside ONE kernel and
+//    nothing is staged in HBM.  Only the few-KB operands that many CTAs re-read (shift vector,
+//    row lists) and the atomically accumulated d_shift go through device scratch.
+//  * STAGED (pageable host memory, or LICV_HOST_ZERO_COPY=0): cudaMemcpyAsync into the slot's
+//    scratch, kernel, cudaMemcpyAsync back; the copy-in of one call overlaps the kernel of the
+//    previous one and the copy-out of the one before.
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -37,6 +48,38 @@ struct Carver {
 };
 
 inline int64_t esize(int dtype) { return dtype == LICV_F32 ? 4 : 2; }
+
+int host_grid_cap() {
+    static const int cap = [] {
+        const char* v = std::getenv("LICV_HOST_GRID_CAP");
+        return v ? std::atoi(v) : 16;
+    }();
+    return cap;
+}
+
+bool zero_copy_enabled() {
+    static const bool on = [] {
+        const char* v = std::getenv("LICV_HOST_ZERO_COPY");
+        return !(v && v[0] == '0');
+    }();
+    return on;
+}
+
+// device-side address of a host buffer the GPU can reach directly (pinned, registered, managed or
+// device memory); nullptr for pageable memory
+template <typename T>
+T* device_view(T* p) {
+    if (!p || !zero_copy_enabled()) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice ||
+        at.type == cudaMemoryTypeManaged)
+        return static_cast<T*>(const_cast<void*>(static_cast<const void*>(at.devicePointer)));
+    return nullptr;
+}
 
 licv_host_session::Slot* acquire(licv_host_session* s) {
     auto* slot = &s->slots[s->next++ % s->slots.size()];
@@ -116,6 +159,18 @@ extern "C" int licv_inject_fwd_host(licv_host_session* s, const void* h, const f
     auto* slot = acquire(s);
     Carver c{slot->scratch, s->bytes};
     const int64_t hb = n_tokens * d * esize(h_dtype), ob = n_tokens * d * esize(out_dtype);
+    {
+        const void* zh = device_view(h);
+        void* zout = device_view(out);
+        if (zh && zout && licv::aligned16(zh) && licv::aligned16(zout)) {   // zero-copy: h is read and out is written over the link by the kernel
+            float* ds = static_cast<float*>(c.take((int64_t)d * 4));
+            if (!c.ok) return LICV_ERR_WORKSPACE;
+            LICV_CUDA(cudaMemcpyAsync(ds, shift, (size_t)d * 4, cudaMemcpyHostToDevice, slot->stream));
+            licv::GridCapScope few_ctas(host_grid_cap());
+            return licv_inject_fwd(zh, ds, zout, n_tokens, d, h_dtype, out_dtype, round_flags,
+                                   reinterpret_cast<licv_stream_t>(slot->stream));
+        }
+    }
     void* dh = c.take(hb);
     float* ds = static_cast<float*>(c.take((int64_t)d * 4));
     void* dout = c.take(ob);
@@ -140,6 +195,25 @@ extern "C" int licv_inject_bwd_host(licv_host_session* s, const void* h, const v
     auto* slot = acquire(s);
     Carver c{slot->scratch, s->bytes};
     const int64_t hb = n_tokens * d * esize(h_dtype), gb = n_tokens * d * esize(g_dtype);
+    if (n_tokens > 0) {
+        const void* zh = device_view(h);
+        const void* zg = device_view(g);
+        void* zdh = dh_out ? device_view(dh_out) : nullptr;
+        if (zh && zg && (!dh_out || zdh) && licv::aligned16(zh) && licv::aligned16(zg) &&
+            licv::aligned16(zdh)) {
+            float* ds = static_cast<float*>(c.take((int64_t)d * 4));
+            float* dds = static_cast<float*>(c.take((int64_t)d * 4));
+            if (!c.ok) return LICV_ERR_WORKSPACE;
+            LICV_CUDA(cudaMemsetAsync(dds, 0, (size_t)d * 4, slot->stream));
+            LICV_CUDA(cudaMemcpyAsync(ds, shift, (size_t)d * 4, cudaMemcpyHostToDevice, slot->stream));
+            licv::GridCapScope few_ctas(host_grid_cap());
+            if (int rc = licv_inject_bwd(zh, zg, ds, zdh, dds, n_tokens, d, h_dtype, g_dtype,
+                                         round_flags, reinterpret_cast<licv_stream_t>(slot->stream)))
+                return rc;
+            LICV_CUDA(cudaMemcpyAsync(d_shift, dds, (size_t)d * 4, cudaMemcpyDeviceToHost, slot->stream));
+            return LICV_OK;
+        }
+    }
     void* dh = c.take(hb);
     void* dg = c.take(gb);
     float* ds = static_cast<float*>(c.take((int64_t)d * 4));
@@ -175,6 +249,29 @@ extern "C" int licv_kd_loss_fwd_bwd_host(licv_host_session* s, const void* stu, 
     auto* slot = acquire(s);
     Carver c{slot->scratch, s->bytes};
     const int64_t sb = n_rows * vocab * esize(dtype), tb = n_tea_rows * vocab * esize(dtype);
+    if (n_rows > 0) {
+        const void* zs = device_view(stu);
+        const void* zt = tea ? device_view(tea) : nullptr;
+        void* zd = dstu ? device_view(dstu) : nullptr;
+        if (zs && (!tea || zt) && (!dstu || zd)) {
+            int32_t* d_ktr = kl_tea_row ? static_cast<int32_t*>(c.take(n_rows * 4 + 4)) : nullptr;
+            int64_t* d_lab = ce_label ? static_cast<int64_t*>(c.take(n_rows * 8 + 8)) : nullptr;
+            float* d_loss = static_cast<float*>(c.take(16));
+            void* d_ws = c.take(licv_kd_loss_workspace_bytes(n_rows));
+            if (!c.ok) return LICV_ERR_WORKSPACE;
+            cudaStream_t st = slot->stream;
+            LICV_CUDA(cudaMemsetAsync(d_ws, 0, 16, st));
+            if (d_ktr) LICV_CUDA(cudaMemcpyAsync(d_ktr, kl_tea_row, (size_t)n_rows * 4, cudaMemcpyHostToDevice, st));
+            if (d_lab) LICV_CUDA(cudaMemcpyAsync(d_lab, ce_label, (size_t)n_rows * 8, cudaMemcpyHostToDevice, st));
+            if (int rc = licv_kd_loss_fwd_bwd(zs, zd, zt, d_ktr, d_lab, nullptr, n_kl, n_ce, temperature,
+                                              kl_eps, hard_loss_weight, only_hard_loss, grad_scale,
+                                              d_loss, d_ws, n_rows, vocab, vocab, vocab, dtype,
+                                              round_flags, reinterpret_cast<licv_stream_t>(st)))
+                return rc;
+            LICV_CUDA(cudaMemcpyAsync(out_losses, d_loss, 12, cudaMemcpyDeviceToHost, st));
+            return LICV_OK;
+        }
+    }
     // device rows are padded to a multiple of 8 elements so that every row starts 16-byte aligned
     void* d_stu = c.take(sb > 0 ? sb : 16);
     void* d_tea = (tea && tb > 0) ? c.take(tb) : nullptr;

@@ -21,7 +21,8 @@ int launch_fwd(const Args& a0, const Launch& L) {
     const int groups = kCtaThreads / L.plan.gt > 0 ? kCtaThreads / L.plan.gt : 1;
     const int threads = groups * L.plan.gt;
     static const int per_sm = resident_ctas_per_sm(kern, kCtaThreads, 0);
-    const int64_t cap = (int64_t)per_sm * device_info().sm_count;
+    int64_t cap = (int64_t)per_sm * device_info().sm_count;
+    if (tl_grid_cap > 0 && tl_grid_cap < cap) cap = tl_grid_cap;
     const int64_t need = ((L.n_tok + TB - 1) / TB + groups - 1) / groups;
     Args a = a0;
     a.gt = L.plan.gt;
@@ -45,7 +46,8 @@ int launch_bwd(const Args& a0, const Launch& L) {
         }
     }
     static const int per_sm = resident_ctas_per_sm(kern, kCtaThreads, 16 * 1024);
-    const int64_t cap = (int64_t)per_sm * device_info().sm_count;
+    int64_t cap = (int64_t)per_sm * device_info().sm_count;
+    if (tl_grid_cap > 0 && tl_grid_cap < cap) cap = tl_grid_cap;
     const int tok_per_group = TB > min_tok ? TB : min_tok;
     const int64_t need = ((L.n_tok + tok_per_group - 1) / tok_per_group + groups - 1) / groups;
     Args a = a0;
@@ -140,7 +142,9 @@ int launch_bwd_pipe(const Args& a, const Launch& L) {
         cap_smem = smem;
         cap_c = C;
     }
-    int64_t grid = pa.n_batches < cap ? pa.n_batches : cap;
+    int64_t lim = cap;
+    if (tl_grid_cap > 0 && tl_grid_cap < lim) lim = tl_grid_cap;
+    int64_t grid = pa.n_batches < lim ? pa.n_batches : lim;
     grid = (grid + C - 1) / C * C;
     cfg.gridDim = dim3((unsigned)grid);
     return (int)cudaLaunchKernelEx(&cfg, kern, pa);

@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(kT, (NV <= 4 ? 3 : 1)) kd_loss_cluster_kernel(
     constexpr int kStep = kT * EPV;                 // elements between a thread's vectors
     extern __shared__ __align__(16) float4 cache[];  // [2][NV * Q][kT]: e_s then e_t / kl_w * w
     __shared__ __align__(16) float4 slots[3][8 * kWarps];   // reduction 1 (two row parities), reduction 2
-    __shared__ __align__(8) uint64_t xbar[2];
+    __shared__ __align__(8) uint64_t xbar[3];   // reduction 1 (two row parities), reduction 2
     __shared__ float s_tot[2 * kWarps];
     __shared__ int s_last;
 
@@ -360,14 +360,16 @@ __global__ void __launch_bounds__(kT, (NV <= 4 ? 3 : 1)) kd_loss_cluster_kernel(
     if (tid == 0) {
         mbar_init(&xbar[0], 1);
         mbar_init(&xbar[1], 1);
+        mbar_init(&xbar[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     cluster_sync_all();   // every peer's barriers exist before the first message
-    // Reduction 1's slots are double-buffered by row parity: on CE-only rows nothing separates
-    // one row's reduction 1 from the next row's, and a fast peer may send its next partial while
-    // a slow warp here still reads the current ones (it cannot get two rows ahead: it needs this
-    // warp's next partial first).
-    Exchange ex1{slots[0], &xbar[0], 0u}, ex2x{slots[2], &xbar[1], 0u};
+    // Reduction 1 has two (slots, mbarrier) sets used alternately by row parity: on CE-only rows
+    // nothing separates one row's reduction 1 from the next row's, so a fast peer may send its
+    // next partial while this CTA has not yet received (or a slow warp here still reads) all the
+    // current ones; it cannot get two rows ahead, because it needs every warp's next partial
+    // first, and a warp sends that only after it is done with the current set.
+    Exchange ex1a{slots[0], &xbar[0], 0u}, ex1b{slots[1], &xbar[1], 0u}, ex2x{slots[2], &xbar[2], 0u};
     uint32_t row_par = 0;
 
     const float T = a.temperature;
@@ -548,7 +550,7 @@ __global__ void __launch_bounds__(kT, (NV <= 4 ? 3 : 1)) kd_loss_cluster_kernel(
             const int tr_nn = fetch_tr(rn + n_clusters), lab_nn = fetch_lab(rn + n_clusters);
 
             // ---- reduction 1: maxima and partition sums of both rows ---------------------------
-            ex1.slots = slots[row_par];
+            Exchange& ex1 = row_par ? ex1b : ex1a;
             row_par ^= 1u;
             {
                 const MZ2 w = mz_warp(mine);

@@ -7,6 +7,8 @@
 
 namespace licv {
 
+thread_local int tl_grid_cap = 0;
+
 const DeviceInfo& device_info() {
     // one entry per device ordinal; a process here drives one GPU, so a small fixed table will do
     static DeviceInfo table[64];

@@ -27,7 +27,8 @@ struct KdArgs {
 int launch_kd_generic(const KdArgs& a, int dtype, cudaStream_t st);
 
 // cluster kernel (licv_kd_loss_cluster.cu): does a row of `vocab` elements fit a cluster, and how
-bool kd_cluster_plan(int vocab, int dtype, float temperature, bool kl_and_ce, int* C, int* NV);
-int launch_kd_cluster(const KdArgs& a, int dtype, int C, int NV, cudaStream_t st);
+bool kd_cluster_plan(int vocab, int dtype, float temperature, bool kl_and_ce, int* C, int* NV,
+                     int* NT);
+int launch_kd_cluster(const KdArgs& a, int dtype, int C, int NV, int NT, cudaStream_t st);
 
 }  // namespace licv

@@ -9,7 +9,8 @@
 // two row-wide reductions between them.  The generic kernel re-reads the 16-bit logits from L2
 // for every sweep and re-evaluates both exponentials each time (~9 MUFU per element: the SFU
 // pipe, not HBM, bounds it at ~20 % of the roofline).  Here a row pair is spread over a
-// thread-block CLUSTER (C CTAs x 256 threads, C x NV x 256 16-byte vectors >= one row):
+// thread-block CLUSTER (C CTAs x NT threads, C x NV x NT 16-byte vectors >= one row; V = 32002
+// 16-bit: 8 CTAs x 128 threads x 4 vectors, six CTAs of different rows per SM):
 //
 //   sweep B  registers (raw logits, prefetched during the previous row) -> e = 2^(u - m_thread)
 //            for student and teacher, written as fp32 to a thread-private shared-memory cache
@@ -22,10 +23,11 @@
 //
 // 4 MUFU per element (2 ex2, 1 rcp, 1 lg2) instead of 9, HBM traffic = the algorithmic 3 e V
 // bytes per KL row (2 e V for a CE-only row, e V zero-fill for a row in neither loss).  The two
-// reductions cross the cluster through distributed shared memory (st.shared::cluster +
-// barrier.cluster).  Three CTAs of different clusters share an SM, so one row's reductions and
-// loads overlap another's arithmetic; the next row's logits are requested before the first
-// reduction of the current one.
+// reductions cross the cluster through distributed shared memory: every warp sends its 16-byte
+// partial to every CTA with st.async, counted on the receiver's mbarrier (no CTA barrier, no
+// cluster barrier, no release fence on the path).  CTAs of different clusters share an SM, so one
+// row's reductions and loads overlap another's arithmetic; the next row's logits are requested
+// while the first reduction's partials travel.
 //
 // Rows may start on any element boundary (V = 32002 / 32003): the student row is walked in
 // 16-byte-aligned vectors, partial first/last vectors go element by element, the teacher row is
@@ -40,8 +42,8 @@
 namespace licv {
 namespace {
 
-constexpr int kT = 256;
-constexpr int kWarps = kT / 32;
+constexpr int kMaxT = 256;            // threads per CTA: 256, or 128 (more, smaller CTAs per SM)
+constexpr int kMaxWarps = kMaxT / 32;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kNoMax = -3.0e38f;   // "no element yet": finite, so differences never give NaN
@@ -87,17 +89,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                  "r"(bytes)
                  : "memory");
 }
+// try_wait with a suspend-time hint: a waiting warp is parked by the hardware instead of
+// re-issuing the probe (spinning warps outrank working ones in the issue arbiter)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "LICV_KD_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra LICV_KD_DONE;\n"
         "bra LICV_KD_WAIT;\n"
         "LICV_KD_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(1000000u)
         : "memory");
 }
 // 16 bytes into slot `local` of CTA `rank`, counted on that CTA's mbarrier `bar`: a one-way
@@ -259,36 +263,40 @@ __device__ __forceinline__ MZ2 mz_join(const MZ2& a, const MZ2& b) {
     r.zt = fmaf(a.zt, pow2i(a.mt - r.mt), b.zt * pow2i(b.mt - r.mt));
     return r;
 }
+// warp-wide join: integer maxima with one REDUX each, every lane rescales its own sum once to
+// the common maximum, then two butterfly sums
 __device__ __forceinline__ MZ2 mz_warp(MZ2 v) {
+    const int ms = __reduce_max_sync(0xffffffffu, v.ms);
+    const int mt = __reduce_max_sync(0xffffffffu, v.mt);
+    float zs = v.zs * pow2i(v.ms - ms);
+    float zt = v.zt * pow2i(v.mt - mt);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        MZ2 b;
-        b.ms = __shfl_xor_sync(0xffffffffu, v.ms, o);
-        b.zs = __shfl_xor_sync(0xffffffffu, v.zs, o);
-        b.mt = __shfl_xor_sync(0xffffffffu, v.mt, o);
-        b.zt = __shfl_xor_sync(0xffffffffu, v.zt, o);
-        v = mz_join(v, b);
+        zs += __shfl_xor_sync(0xffffffffu, zs, o);
+        zt += __shfl_xor_sync(0xffffffffu, zt, o);
     }
-    return v;
+    return MZ2{ms, zs, mt, zt};
 }
 
 struct Exchange {
-    float4* slots;      // [C * kWarps] partials in THIS CTA's shared memory
-    uint64_t* bar;      // completes when C * kWarps * 16 bytes have arrived
+    float4* slots;      // [C * W] partials in THIS CTA's shared memory (W = warps per CTA)
+    uint64_t* bar;      // completes when C * W * 16 bytes have arrived
     uint32_t parity;
 };
 
 // this warp's partial -> slot (rank, warp) of every CTA of the cluster
+template <int W>
 __device__ __forceinline__ void exchange_send(const Exchange& x, float4 v, uint32_t rank, uint32_t C) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) mbar_expect_tx(x.bar, C * kWarps * 16u);
-    if ((uint32_t)lane < C) st_async_f4(x.slots + rank * kWarps + warp, x.bar, (uint32_t)lane, v);
+    if (threadIdx.x == 0) mbar_expect_tx(x.bar, C * W * 16u);
+    if ((uint32_t)lane < C) st_async_f4(x.slots + rank * W + warp, x.bar, (uint32_t)lane, v);
 }
+template <int W>
 __device__ __forceinline__ MZ2 exchange_recv_mz(Exchange& x, uint32_t C) {
     const int lane = threadIdx.x & 31;
     mbar_wait(x.bar, x.parity);
     x.parity ^= 1u;
-    const int n = (int)C * kWarps;
+    const int n = (int)C * W;
     MZ2 v{kNoMaxI, 0.f, kNoMaxI, 0.f};
     if (lane < n) {
         const float4 p = x.slots[lane];
@@ -300,11 +308,12 @@ __device__ __forceinline__ MZ2 exchange_recv_mz(Exchange& x, uint32_t C) {
     }
     return mz_warp(v);
 }
+template <int W>
 __device__ __forceinline__ float2 exchange_recv_sum(Exchange& x, uint32_t C) {
     const int lane = threadIdx.x & 31;
     mbar_wait(x.bar, x.parity);
     x.parity ^= 1u;
-    const int n = (int)C * kWarps;
+    const int n = (int)C * W;
     float2 v = make_float2(0.f, 0.f);
     if (lane < n) {
         const float4 p = x.slots[lane];
@@ -338,14 +347,16 @@ __device__ long long g_trace[64 * 64 * 8];
 constexpr int kLabNone = -100;            // not a CE row
 constexpr int kLabBad = 0x7fffffff;       // a label outside int32: out of range for any V
 
-template <int DT, int NV>
-__global__ void __launch_bounds__(kT, (NV <= 4 ? 3 : 1)) kd_loss_cluster_kernel(KdArgs a) {
+template <int DT, int NV, int NT>
+__global__ void __launch_bounds__(NT, (NV <= 4 ? 768 / NT : 1)) kd_loss_cluster_kernel(KdArgs a) {
+    constexpr int kT = NT;
+    constexpr int kWarps = NT / 32;
     constexpr int EPV = Fmt<DT>::kPerVec;
     constexpr int EB = Fmt<DT>::kBytes;
     constexpr int Q = EPV / 4;                      // float4 slots per vector
     constexpr int kStep = kT * EPV;                 // elements between a thread's vectors
     extern __shared__ __align__(16) float4 cache[];  // [2][NV * Q][kT]: e_s then e_t / kl_w * w
-    __shared__ __align__(16) float4 slots[3][8 * kWarps];   // reduction 1 (two row parities), reduction 2
+    __shared__ __align__(16) float4 slots[3][8 * kMaxWarps];   // reduction 1 (two row parities), reduction 2
     __shared__ __align__(8) uint64_t xbar[3];   // reduction 1 (two row parities), reduction 2
     __shared__ float s_tot[2 * kWarps];
     __shared__ int s_last;
@@ -394,9 +405,11 @@ __global__ void __launch_bounds__(kT, (NV <= 4 ? 3 : 1)) kd_loss_cluster_kernel(
         if (!use_kl || r >= a.n_rows) return -1;
         return a.kl_tea_row ? a.kl_tea_row[r] : (int)r;
     };
-    auto fetch_lab = [&](int64_t r) -> int {
+    auto fetch_lab = [&](int64_t r) -> int64_t {     // raw: converted where it is first needed
         if (!use_ce || r >= a.n_rows) return kLabNone;
-        const int64_t l = a.ce_label[r];
+        return a.ce_label[r];
+    };
+    auto narrow_lab = [](int64_t l) -> int {
         return (l < -100 || l > 0x7fffffff) ? kLabBad : (int)l;
     };
     auto x_row = [&](int64_t r) { return static_cast<const char*>(a.stu) + (size_t)r * a.stu_stride * EB; };
@@ -498,9 +511,10 @@ __global__ void __launch_bounds__(kT, (NV <= 4 ? 3 : 1)) kd_loss_cluster_kernel(
     // software pipeline over this cluster's rows: the raw logits of row `r` are in registers,
     // (tr_n, lab_n) describe the row after it
     int64_t r = cluster_id;
-    int tr = fetch_tr(r), lab = fetch_lab(r);
+    int tr = fetch_tr(r), lab = narrow_lab(fetch_lab(r));
     if (r < a.n_rows) load_raw(r, tr, lab);
-    int tr_n = fetch_tr(r + n_clusters), lab_n = fetch_lab(r + n_clusters);
+    int tr_n = fetch_tr(r + n_clusters);
+    int64_t lab_n = fetch_lab(r + n_clusters);
 #ifdef LICV_TRACE
     int trace_row = -1;
 #endif
@@ -544,21 +558,22 @@ __global__ void __launch_bounds__(kT, (NV <= 4 ? 3 : 1)) kd_loss_cluster_kernel(
                 mine.zt = sweep_b(xt, (float)mine.mt, c_row, it_row, rnd_row, ct);
             }
             LICV_TP(1);
-            // ---- the raw registers are free: request the next row now; it lands during the
-            //      reductions and sweeps below.  Then look up the row after that. ---------------
-            if (rn < a.n_rows) load_raw(rn, tr_n, lab_n);
-            const int tr_nn = fetch_tr(rn + n_clusters), lab_nn = fetch_lab(rn + n_clusters);
-
-            // ---- reduction 1: maxima and partition sums of both rows ---------------------------
+            // ---- reduction 1: maxima and partition sums of both rows.  The partial is sent
+            //      first; the request for the next row's logits (the raw registers are free now)
+            //      is issued while the partials travel, and lands during the sweeps below. -------
             Exchange& ex1 = row_par ? ex1b : ex1a;
             row_par ^= 1u;
             {
                 const MZ2 w = mz_warp(mine);
-                exchange_send(ex1, make_float4(__int_as_float(w.ms), w.zs, __int_as_float(w.mt), w.zt),
+                exchange_send<kWarps>(ex1, make_float4(__int_as_float(w.ms), w.zs, __int_as_float(w.mt), w.zt),
                               rank, C);
             }
+            const int lab_next = narrow_lab(lab_n);
+            if (rn < a.n_rows) load_raw(rn, tr_n, lab_next);
+            const int tr_nn = fetch_tr(rn + n_clusters);
+            const int64_t lab_nn = fetch_lab(rn + n_clusters);
             LICV_TP(2);
-            const MZ2 tot = exchange_recv_mz(ex1, C);
+            const MZ2 tot = exchange_recv_mz<kWarps>(ex1, C);
             LICV_TP(3);
             const float fs = pow2i(mine.ms - tot.ms) * rcp(tot.zs);      // q = e_s * fs
 
@@ -592,8 +607,8 @@ __global__ void __launch_bounds__(kT, (NV <= 4 ? 3 : 1)) kd_loss_cluster_kernel(
                 }
                 LICV_TP(4);
                 // ---- reduction 2: KL_n and W_n --------------------------------------------------
-                exchange_send(ex2x, make_float4(warp_sum(klp), warp_sum(wp), 0.f, 0.f), rank, C);
-                const float2 r2 = exchange_recv_sum(ex2x, C);
+                exchange_send<kWarps>(ex2x, make_float4(warp_sum(klp), warp_sum(wp), 0.f, 0.f), rank, C);
+                const float2 r2 = exchange_recv_sum<kWarps>(ex2x, C);
                 LICV_TP(5);
                 kl_row = r2.x * kLn2;
                 W = r2.y;
@@ -640,13 +655,13 @@ __global__ void __launch_bounds__(kT, (NV <= 4 ? 3 : 1)) kd_loss_cluster_kernel(
                 row_ce[r] = ce;
             }
             r = rn;
-            tr = tr_n; lab = lab_n;
+            tr = tr_n; lab = lab_next;
             tr_n = tr_nn; lab_n = lab_nn;
             continue;
         }
         // (row in neither loss) advance: nothing was prefetched for the next row yet
         r = rn;
-        tr = tr_n; lab = lab_n;
+        tr = tr_n; lab = narrow_lab(lab_n);
         if (r < a.n_rows) load_raw(r, tr, lab);
         tr_n = fetch_tr(r + n_clusters); lab_n = fetch_lab(r + n_clusters);
     }
@@ -689,20 +704,20 @@ inline int env_int(const char* name, int dflt) {
     return v ? std::atoi(v) : dflt;
 }
 
-template <int DT, int NV>
+template <int DT, int NV, int NT>
 int launch_cluster(const KdArgs& a, int C, cudaStream_t st) {
-    auto kern = kd_loss_cluster_kernel<DT, NV>;
-    constexpr size_t smem = (size_t)2 * NV * Fmt<DT>::kPerVec * kT * sizeof(float);
+    auto kern = kd_loss_cluster_kernel<DT, NV, NT>;
+    constexpr size_t smem = (size_t)2 * NV * Fmt<DT>::kPerVec * NT * sizeof(float);
     static bool raised = false;
     if (!raised && smem > 48 * 1024) {
         const cudaError_t e =
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    if (!raised && C > 8) return LICV_ERR_BAD_ARGUMENT;
+    if (C > 8) return LICV_ERR_BAD_ARGUMENT;
     raised = true;
     cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(kT);
+    cfg.blockDim = dim3(NT);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -722,7 +737,7 @@ int launch_cluster(const KdArgs& a, int C, cudaStream_t st) {
         } else {
             cudaGetLastError();
             int per_sm = 1;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kT, smem) != cudaSuccess ||
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess ||
                 per_sm < 1)
                 per_sm = 1;
             cap[C] = (int64_t)per_sm * device_info().sm_count / C;
@@ -736,12 +751,18 @@ int launch_cluster(const KdArgs& a, int C, cudaStream_t st) {
 }
 
 template <int DT>
-int dispatch_nv(const KdArgs& a, int C, int NV, cudaStream_t st) {
+int dispatch_nv(const KdArgs& a, int C, int NV, int NT, cudaStream_t st) {
+    if (NT == 128) {
+        switch (NV) {
+            case 4: return launch_cluster<DT, 4, 128>(a, C, st);
+            default: return LICV_ERR_BAD_ARGUMENT;
+        }
+    }
     switch (NV) {
-        case 1: return launch_cluster<DT, 1>(a, C, st);
-        case 2: return launch_cluster<DT, 2>(a, C, st);
-        case 4: return launch_cluster<DT, 4>(a, C, st);
-        default: return launch_cluster<DT, 8>(a, C, st);
+        case 1: return launch_cluster<DT, 1, 256>(a, C, st);
+        case 2: return launch_cluster<DT, 2, 256>(a, C, st);
+        case 4: return launch_cluster<DT, 4, 256>(a, C, st);
+        default: return launch_cluster<DT, 8, 256>(a, C, st);
     }
 }
 
@@ -753,27 +774,34 @@ extern "C" int licv_debug_read_trace(long long* host, int n) {
 }
 #endif
 
-bool kd_cluster_plan(int vocab, int dtype, float temperature, bool kl_and_ce, int* C, int* NV) {
+bool kd_cluster_plan(int vocab, int dtype, float temperature, bool kl_and_ce, int* C, int* NV,
+                     int* NT) {
     static const int off = env_int("LICV_KD_NO_CLUSTER", 0);
+    static const int small_ctas = env_int("LICV_KD_THREADS", 128);   // 128: six 4-warp CTAs per SM
     if (off) return false;
     // a KL + CE row at T != 1 needs a third exponential stream (CE works on the raw logits):
     // left to the generic kernel
     if (kl_and_ce && temperature != 1.0f) return false;
     const int epv = dtype == LICV_F32 ? 4 : 8;
     const int64_t need = ((int64_t)vocab + epv - 1) / epv + 1;   // + 1: a row may straddle
+    *NT = 256;
+    if (small_ctas == 128 && (int64_t)8 * 4 * 128 >= need && (int64_t)4 * 4 * 128 < need) {
+        *C = 8; *NV = 4; *NT = 128;    // rows of 2049..4096 vectors: 8 CTAs x 128 threads x 4
+        return true;
+    }
     for (int nv = 1; nv <= 4; nv *= 2)
-        if ((int64_t)nv * kT >= need) { *C = 1; *NV = nv; return true; }
+        if ((int64_t)nv * kMaxT >= need) { *C = 1; *NV = nv; return true; }
     for (int c = 2; c <= 8; c *= 2)
-        if ((int64_t)c * 4 * kT >= need) { *C = c; *NV = 4; return true; }
-    if ((int64_t)8 * 8 * kT >= need) { *C = 8; *NV = 8; return true; }
+        if ((int64_t)c * 4 * kMaxT >= need) { *C = c; *NV = 4; return true; }
+    if ((int64_t)8 * 8 * kMaxT >= need) { *C = 8; *NV = 8; return true; }
     return false;
 }
 
-int launch_kd_cluster(const KdArgs& a, int dtype, int C, int NV, cudaStream_t st) {
+int launch_kd_cluster(const KdArgs& a, int dtype, int C, int NV, int NT, cudaStream_t st) {
     switch (dtype) {
-        case LICV_F32: return dispatch_nv<LICV_F32>(a, C, NV, st);
-        case LICV_BF16: return dispatch_nv<LICV_BF16>(a, C, NV, st);
-        default: return dispatch_nv<LICV_F16>(a, C, NV, st);
+        case LICV_F32: return dispatch_nv<LICV_F32>(a, C, NV, NT, st);
+        case LICV_BF16: return dispatch_nv<LICV_BF16>(a, C, NV, NT, st);
+        default: return dispatch_nv<LICV_F16>(a, C, NV, NT, st);
     }
 }
 

@@ -680,8 +680,17 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        torch.cuda.synchronize()
         torch.distributed.barrier()
+        # teardown must not be able to hang the launcher: the line is out, everything is
+        # synchronised; a watchdog ends the process if NCCL / CUDA-graph destructors stall
+        sys.stdout.flush()
+        sys.stderr.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        graph = None
+        torch.cuda.synchronize()
         torch.distributed.destroy_process_group()
+        os._exit(0)
     return 0
 
 

@@ -259,6 +259,17 @@ def time_kernel_launches(fn_list, stream):
     return [e0.elapsed_time(e1) * 1e-3 for e0, e1 in evs]
 
 
+def load_traffic(key):
+    """dram__bytes_read + dram__bytes_write per launch of `key` from the committed ncu capture
+    (profiles/r1_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)[key]
+        return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def load_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -614,7 +625,11 @@ def main():
         bytes_kd = es * CFG["vocab"] * (3 * n_kl_rows + 2 * (n_ce_rows - n_kl_rows) + n_dead)
         roofline = {"bound": "hbm", "kernel": "licv_inject_bwd",
                     "achieved": bytes_bwd / t_bwd / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": bytes_bwd / t_bwd / 1e9 / peak, "traffic": None,
+                    "frac": bytes_bwd / t_bwd / 1e9 / peak,
+                    "traffic": load_traffic("licv_inject_bwd@256tok"),
+                    "traffic_note": "ncu --set full capture of the same launch shape (bf16): DRAM "
+                                    "reads = the algorithmic h + g; the dh write-back is still in "
+                                    "L2 when the kernel ends",
                     "peak_source": peak_src, "bytes_per_launch": bytes_bwd,
                     "us_per_launch": t_bwd * 1e6, "launches_per_step": L,
                     "share_of_step": L * t_bwd / (ms_per_step * 1e-3),

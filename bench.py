@@ -429,23 +429,26 @@ def run_e2e_host(hp, steps, warmup, seed):
     sess = C.c_void_p()
     scratch = max(3 * n_tok * d * es + 4 * d * 4 + 4096,
                   (n_tok + B * T4) * V * es + n_tok * 16 + 65536) + (1 << 20)
-    n_slots = env_int("LICV_E2E_SLOTS", 8)
+    n_slots = env_int("LICV_E2E_SLOTS", 16)
     hp.abi.check(lib.licv_host_session_create(C.byref(sess), scratch, n_slots), "host_session_create")
 
     def step():
         for l in range(L):
-            hp.abi.check(lib.licv_inject_fwd_host(sess, hb["h"][l].data_ptr(), icv_h[l].data_ptr(),
-                                                  out_h[l].data_ptr(), n_tok, d, hp.code, hp.code,
-                                                  hp.flags), "inject_fwd_host")
+            # the forward keeps h on the device for its backward (saved-for-backward), so the
+            # backward moves only g in and dh out
+            hp.abi.check(lib.licv_inject_fwd_host_save(sess, l, hb["h"][l].data_ptr(),
+                                                       icv_h[l].data_ptr(), out_h[l].data_ptr(),
+                                                       n_tok, d, hp.code, hp.code, hp.flags),
+                         "inject_fwd_host_save")
         hp.abi.check(lib.licv_kd_loss_fwd_bwd_host(
             sess, hb["stu"].data_ptr(), dstu_h.data_ptr(), hb["tea"].data_ptr(), ktr.data_ptr(),
             lab.data_ptr(), n_kl, n_ce, CFG["temperature"], CFG["kl_eps"], CFG["hard_loss_weight"],
             0, 1.0, loss_h.data_ptr(), n_tok, B * T4, V, hp.code, 16), "kd_loss_host")
         for l in reversed(range(L)):
-            hp.abi.check(lib.licv_inject_bwd_host(sess, hb["h"][l].data_ptr(), hb["g"][l].data_ptr(),
-                                                  icv_h[l].data_ptr(), dh_h[l].data_ptr(),
-                                                  ds_h[l].data_ptr(), n_tok, d, hp.code, hp.code,
-                                                  hp.flags), "inject_bwd_host")
+            hp.abi.check(lib.licv_inject_bwd_host_saved(sess, l, hb["g"][l].data_ptr(),
+                                                        icv_h[l].data_ptr(), dh_h[l].data_ptr(),
+                                                        ds_h[l].data_ptr(), n_tok, d, hp.code,
+                                                        hp.code, hp.flags), "inject_bwd_host_saved")
         hp.abi.check(lib.licv_host_sync(sess), "host_sync")
         return float(loss_h[2])   # the device->host read of the step's result
 
@@ -456,6 +459,8 @@ def run_e2e_host(hp, steps, warmup, seed):
         step()
     dt = (time.perf_counter() - t0) / steps
     lib.licv_host_session_destroy(sess)
+    # bytes that actually cross the link per step: h (once) and g per layer, the shift twice,
+    # student + teacher logits, the two row lists; back: out and dh per layer, d_shift, d(logits)
     h2d = L * (2 * n_tok * d * es + 2 * d * 4) + (n_tok + B * T4) * V * es + n_tok * 12
     d2h = L * (2 * n_tok * d * es + d * 4) + n_tok * V * es + 12
     return dt, h2d, d2h

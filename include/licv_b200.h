@@ -178,10 +178,11 @@ int licv_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_
 
 /* ------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a host-side plugin of the reference would call): inputs and
- * outputs live in HOST memory (pinned memory makes the copies asynchronous); the call stages
- * them through device scratch owned by the session, runs the same kernels and copies the
- * results back.  Calls on one session are pipelined on internal streams (copy-in of call k+1
- * overlaps the kernel of call k and the copy-out of call k-1); licv_host_sync waits for all.
+ * outputs live in HOST memory.  Pinned / registered buffers are read and written by the kernels
+ * directly over the host link (zero-copy: both directions busy inside one kernel, nothing staged
+ * in HBM); pageable buffers are staged through device scratch owned by the session with
+ * cudaMemcpyAsync.  Calls on one session are pipelined on internal streams; licv_host_sync waits
+ * for all of them.  One session is driven by one host thread at a time.
  * ------------------------------------------------------------------------------------------ */
 typedef struct licv_host_session licv_host_session;
 int licv_host_session_create(licv_host_session** out, int64_t scratch_bytes_per_slot, int n_slots);
@@ -195,6 +196,17 @@ int licv_inject_fwd_host(licv_host_session* s, const void* h, const float* shift
 int licv_inject_bwd_host(licv_host_session* s, const void* h, const void* g, const float* shift,
                          void* dh, float* d_shift /* [d], overwritten */, int64_t n_tokens, int d,
                          int h_dtype, int g_dtype, unsigned round_flags);
+/* Forward that keeps its hidden states on the device for the matching backward (what autograd's
+ * "saved for backward" is on a GPU): the backward then moves only g in and dh out.  `key` names
+ * the pair (e.g. the layer index); a second save under a live key replaces it; the saved copy
+ * is released by the backward that uses it.  licv_inject_bwd_host_saved returns
+ * LICV_ERR_BAD_ARGUMENT when no forward was saved under `key`. */
+int licv_inject_fwd_host_save(licv_host_session* s, int64_t key, const void* h, const float* shift,
+                              void* out, int64_t n_tokens, int d, int h_dtype, int out_dtype,
+                              unsigned round_flags);
+int licv_inject_bwd_host_saved(licv_host_session* s, int64_t key, const void* g, const float* shift,
+                               void* dh, float* d_shift /* [d], overwritten */, int64_t n_tokens,
+                               int d, int h_dtype, int g_dtype, unsigned round_flags);
 int licv_kd_loss_fwd_bwd_host(licv_host_session* s, const void* stu, void* dstu, const void* tea,
                               const int32_t* kl_tea_row, const int64_t* ce_label, int64_t n_kl,
                               int64_t n_ce, float temperature, float kl_eps, float hard_loss_weight,

@@ -45,6 +45,9 @@ SIGNATURES = {
     "licv_host_free_pinned": (None, [_vp]),
     "licv_inject_fwd_host": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _u32]),
     "licv_inject_bwd_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _u32]),
+    "licv_inject_fwd_host_save": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _u32]),
+    "licv_inject_bwd_host_saved": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32,
+                                          _u32]),
     "licv_kd_loss_fwd_bwd_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32,
                                          _f32, _i32, _f32, _vp, _i64, _i64, _i32, _i32, _u32]),
 }

@@ -14,6 +14,7 @@
 //    previous one and the copy-out of the one before.
 #include <cstdlib>
 #include <new>
+#include <unordered_map>
 #include <vector>
 
 #include "licv_common.cuh"
@@ -23,9 +24,17 @@ struct licv_host_session {
         char* scratch = nullptr;
         cudaStream_t stream = nullptr;
     };
+    // hidden states kept on the device between a forward and its backward ("saved for backward")
+    struct Saved {
+        void* dev = nullptr;
+        int64_t bytes = 0;          // capacity
+        cudaEvent_t ready = nullptr;   // recorded after the last use (write by fwd / read by bwd)
+    };
     std::vector<Slot> slots;
     int64_t bytes = 0;
     uint64_t next = 0;
+    std::unordered_map<int64_t, Saved> saved;   // key -> buffer holding that forward's h
+    std::vector<Saved> free_list;               // released buffers, reused by size
 };
 
 namespace {
@@ -125,6 +134,14 @@ extern "C" int licv_host_session_destroy(licv_host_session* s) {
             cudaStreamDestroy(slot.stream);
         }
         if (slot.scratch) cudaFree(slot.scratch);
+    }
+    for (auto& kv : s->saved) {
+        if (kv.second.ready) cudaEventDestroy(kv.second.ready);
+        if (kv.second.dev) cudaFree(kv.second.dev);
+    }
+    for (auto& b : s->free_list) {
+        if (b.ready) cudaEventDestroy(b.ready);
+        if (b.dev) cudaFree(b.dev);
     }
     delete s;
     return LICV_OK;
@@ -232,6 +249,108 @@ extern "C" int licv_inject_bwd_host(licv_host_session* s, const void* h, const v
             LICV_CUDA(cudaMemcpyAsync(dh_out, ddh, (size_t)hb, cudaMemcpyDeviceToHost, slot->stream));
     }
     LICV_CUDA(cudaMemcpyAsync(d_shift, dds, (size_t)d * 4, cudaMemcpyDeviceToHost, slot->stream));
+    return LICV_OK;
+}
+
+// ---- forward that keeps h on the device for its backward -------------------------------------
+extern "C" int licv_inject_fwd_host_save(licv_host_session* s, int64_t key, const void* h,
+                                         const float* shift, void* out, int64_t n_tokens, int d,
+                                         int h_dtype, int out_dtype, unsigned round_flags) {
+    if (!s) return LICV_ERR_NULL_POINTER;
+    if (n_tokens <= 0 || d <= 0) return LICV_ERR_BAD_ARGUMENT;
+    if (!h || !shift || !out) return LICV_ERR_NULL_POINTER;
+    const int64_t hb = n_tokens * d * esize(h_dtype), ob = n_tokens * d * esize(out_dtype);
+    // a buffer for this key: the key's previous one, else a released one that is large enough
+    licv_host_session::Saved buf;
+    auto it = s->saved.find(key);
+    if (it != s->saved.end()) {
+        buf = it->second;
+        s->saved.erase(it);
+    }
+    if (buf.bytes < hb) {
+        if (buf.dev) s->free_list.push_back(buf);
+        buf = licv_host_session::Saved();
+        for (size_t i = 0; i < s->free_list.size(); ++i) {
+            if (s->free_list[i].bytes >= hb) {
+                buf = s->free_list[i];
+                s->free_list.erase(s->free_list.begin() + i);
+                break;
+            }
+        }
+    }
+    if (!buf.dev) {
+        LICV_CUDA(cudaMalloc(&buf.dev, (size_t)hb));
+        buf.bytes = hb;
+        LICV_CUDA(cudaEventCreateWithFlags(&buf.ready, cudaEventDisableTiming));
+        LICV_CUDA(cudaEventRecord(buf.ready, nullptr));
+    }
+    auto* slot = acquire(s);
+    Carver c{slot->scratch, s->bytes};
+    float* ds = static_cast<float*>(c.take((int64_t)d * 4));
+    void* zout = device_view(out);
+    void* dout = (zout && licv::aligned16(zout)) ? zout : c.take(ob);
+    if (!c.ok) {
+        s->free_list.push_back(buf);
+        return LICV_ERR_WORKSPACE;
+    }
+    cudaStream_t st = slot->stream;
+    int rc = (int)cudaStreamWaitEvent(st, buf.ready, 0);   // the buffer's previous user is done
+    if (!rc) rc = (int)cudaMemcpyAsync(buf.dev, h, (size_t)hb, cudaMemcpyHostToDevice, st);
+    if (!rc) rc = (int)cudaMemcpyAsync(ds, shift, (size_t)d * 4, cudaMemcpyHostToDevice, st);
+    if (!rc) {
+        licv::GridCapScope few_ctas(dout == zout ? host_grid_cap() : 0);
+        rc = licv_inject_fwd(buf.dev, ds, dout, n_tokens, d, h_dtype, out_dtype, round_flags,
+                             reinterpret_cast<licv_stream_t>(st));
+    }
+    if (!rc && dout != zout) rc = (int)cudaMemcpyAsync(out, dout, (size_t)ob, cudaMemcpyDeviceToHost, st);
+    if (!rc) rc = (int)cudaEventRecord(buf.ready, st);
+    if (rc) {
+        s->free_list.push_back(buf);
+        return rc;
+    }
+    s->saved[key] = buf;
+    return LICV_OK;
+}
+
+extern "C" int licv_inject_bwd_host_saved(licv_host_session* s, int64_t key, const void* g,
+                                          const float* shift, void* dh_out, float* d_shift,
+                                          int64_t n_tokens, int d, int h_dtype, int g_dtype,
+                                          unsigned round_flags) {
+    if (!s) return LICV_ERR_NULL_POINTER;
+    if (n_tokens <= 0 || d <= 0) return LICV_ERR_BAD_ARGUMENT;
+    if (!g || !shift || !d_shift) return LICV_ERR_NULL_POINTER;
+    auto it = s->saved.find(key);
+    const int64_t hb = n_tokens * d * esize(h_dtype), gb = n_tokens * d * esize(g_dtype);
+    if (it == s->saved.end() || it->second.bytes < hb) return LICV_ERR_BAD_ARGUMENT;   // no such forward
+    licv_host_session::Saved buf = it->second;
+    auto* slot = acquire(s);
+    Carver c{slot->scratch, s->bytes};
+    float* ds = static_cast<float*>(c.take((int64_t)d * 4));
+    float* dds = static_cast<float*>(c.take((int64_t)d * 4));
+    const void* zg = device_view(g);
+    void* zdh = dh_out ? device_view(dh_out) : nullptr;
+    const bool zero_copy = zg && licv::aligned16(zg) && (!dh_out || (zdh && licv::aligned16(zdh)));
+    void* dg = zero_copy ? const_cast<void*>(zg) : c.take(gb);
+    void* ddh = !dh_out ? nullptr : (zero_copy ? zdh : c.take(hb));
+    if (!c.ok) return LICV_ERR_WORKSPACE;
+    cudaStream_t st = slot->stream;
+    LICV_CUDA(cudaStreamWaitEvent(st, buf.ready, 0));        // the forward's copy of h has landed
+    LICV_CUDA(cudaMemsetAsync(dds, 0, (size_t)d * 4, st));
+    LICV_CUDA(cudaMemcpyAsync(ds, shift, (size_t)d * 4, cudaMemcpyHostToDevice, st));
+    if (!zero_copy) LICV_CUDA(cudaMemcpyAsync(dg, g, (size_t)gb, cudaMemcpyHostToDevice, st));
+    {
+        licv::GridCapScope few_ctas(zero_copy ? host_grid_cap() : 0);
+        if (int rc = licv_inject_bwd(buf.dev, dg, ds, ddh, dds, n_tokens, d, h_dtype, g_dtype,
+                                     round_flags, reinterpret_cast<licv_stream_t>(st)))
+            return rc;
+    }
+    if (dh_out && !zero_copy)
+        LICV_CUDA(cudaMemcpyAsync(dh_out, ddh, (size_t)hb, cudaMemcpyDeviceToHost, st));
+    LICV_CUDA(cudaMemcpyAsync(d_shift, dds, (size_t)d * 4, cudaMemcpyDeviceToHost, st));
+    // the saved h is consumed: its buffer may be reused once this backward has run
+    LICV_CUDA(cudaEventRecord(buf.ready, st));
+    s->saved.erase(it);
+    s->free_list.push_back(buf);
     return LICV_OK;
 }
 

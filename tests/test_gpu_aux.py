@@ -192,6 +192,26 @@ def test_host_entry_points_match_device_entry_points(ops):
         _abi.check(lib.licv_inject_bwd_host(sess, h.data_ptr(), g.data_ptr(), s.data_ptr(),
                                             dh_h.data_ptr(), ds_h.data_ptr(), n_tok, d, code, code, 0),
                    "bwd_host")
+        # saved-for-backward pair: h crosses the link once, the backward takes only g
+        out2 = torch.empty_like(h).pin_memory()
+        dh2 = torch.empty_like(h).pin_memory()
+        ds2 = torch.empty(d).pin_memory()
+        assert lib.licv_inject_bwd_host_saved(sess, 7, g.data_ptr(), s.data_ptr(), dh2.data_ptr(),
+                                              ds2.data_ptr(), n_tok, d, code, code, 0) == -5  # nothing saved
+        for key in (7, 7, 8):      # a second save under a live key replaces it
+            _abi.check(lib.licv_inject_fwd_host_save(sess, key, h.data_ptr(), s.data_ptr(), out2.data_ptr(),
+                                                     n_tok, d, code, code, 0), "fwd_host_save")
+        _abi.check(lib.licv_inject_bwd_host_saved(sess, 7, g.data_ptr(), s.data_ptr(), dh2.data_ptr(),
+                                                  ds2.data_ptr(), n_tok, d, code, code, 0), "bwd_host_saved")
+        # pageable (not pinned) host buffers take the staged path
+        h_pg, g_pg = h.clone(), g.clone()
+        out3, dh3, ds3 = torch.empty_like(h_pg), torch.empty_like(h_pg), torch.empty(d)
+        assert not h_pg.is_pinned()
+        _abi.check(lib.licv_inject_fwd_host_save(sess, 9, h_pg.data_ptr(), s.data_ptr(), out3.data_ptr(),
+                                                 n_tok, d, code, code, 0), "fwd_host_save pageable")
+        _abi.check(lib.licv_inject_bwd_host_saved(sess, 9, g_pg.data_ptr(), s.data_ptr(), dh3.data_ptr(),
+                                                  ds3.data_ptr(), n_tok, d, code, code, 0),
+                   "bwd_host_saved pageable")
         stu = (torch.tensor(rng.normal(size=(R, V)), dtype=torch.float32) * 3).to(dt).pin_memory()
         tea = (torch.tensor(rng.normal(size=(Rt, V)), dtype=torch.float32) * 3).to(dt).pin_memory()
         ktr = torch.tensor([0, -1, 1, 2, -1, -1, 3, 4, -1], dtype=torch.int32).pin_memory()
@@ -211,6 +231,9 @@ def test_host_entry_points_match_device_entry_points(ops):
     dh_d = ops.inject_backward(h.cuda(), g.cuda(), sd, ds_d, True, 0)
     assert torch.equal(out_h.cuda(), out_d) and torch.equal(dh_h.cuda(), dh_d)
     assert rel_err(host(ds_h), host(ds_d)) < 1e-6          # atomics: order may differ
+    assert torch.equal(out2.cuda(), out_d) and torch.equal(dh2.cuda(), dh_d)
+    assert torch.equal(out3.cuda(), out_d) and torch.equal(dh3.cuda(), dh_d)
+    assert rel_err(host(ds2), host(ds_d)) < 1e-6 and rel_err(host(ds3), host(ds_d)) < 1e-6
     losses, dstu_d = ops.kd_loss_raw(stu.cuda(), tea.cuda(), ktr.cuda(), lab.cuda(), None, 5, 8, 1.0,
                                      1e-6, 0.5, in_place=False)
     assert torch.equal(dstu_h.cuda(), dstu_d)

@@ -216,3 +216,51 @@ def test_inject_full_size_properties(ops):
         ops.inject_backward(h[i * step:(i + 1) * step], g1[i * step:(i + 1) * step], shift, acc,
                             False, 0)
     assert rel_err(host(acc), host(ds1)) < 1e-4
+
+
+# BASELINE.json configs 2-5 at their own shapes: the fp16 DeepSpeed recipe of
+# idefics-9B, the bf16 MLP-output hook of idefics2 (1 and 5 image crops), and the inference sweep
+# (beams x batch x T, prefill and single-token decode)
+CONFIG_SHAPES = [
+    ("cfg2_idefics9b_fp16_ds", 8 * 32, "fp16", "lowp_chain"),
+    ("cfg3_idefics2_bf16_1crop", 8 * 96, "bf16", "mixed_autocast"),
+    ("cfg3_idefics2_bf16_5crops", 8 * 352, "bf16", "mixed_autocast"),
+    ("cfg5_decode_bs1_beams3", 3, "bf16", "none"),
+    ("cfg5_decode_bs64_beams3", 192, "bf16", "none"),
+    ("cfg5_prefill_bs8_beams3_t128", 24 * 128, "bf16", "none"),
+    ("cfg5_prefill_bs2_beams3_t2048", 6 * 2048, "fp16", "none"),
+]
+
+
+@pytest.mark.parametrize("name,n_tok,hdt,chain", CONFIG_SHAPES)
+def test_inject_baseline_config_shapes(ops, name, n_tok, hdt, chain):
+    from licv_vqa_b200 import _abi
+    d = 4096
+    rng = np.random.default_rng(len(name) * 31 + n_tok)
+    sigma = rng.uniform(1, 30, size=(n_tok, 1))
+    hn = rng.normal(size=(n_tok, d)) * sigma
+    hn[:, [7, 2041]] *= 100.0                      # LLaMA-style massive-activation channels
+    h = dev(hn, TD[hdt])
+    hn = host(h)
+    s = rng.normal(size=d)
+    s = s / np.linalg.norm(s) * np.linalg.norm(hn, axis=-1).mean() * 0.1
+    flags = {"none": 0,
+             "lowp_chain": _abi.ROUND_Y | _abi.ROUND_NH | _abi.ROUND_NY | _abi.ROUND_T,
+             "mixed_autocast": 0}[chain]
+    if chain == "lowp_chain":
+        s = host(dev(s, TD[hdt]))                  # the ICV itself is low precision in this recipe
+    odt = "fp32" if chain == "mixed_autocast" else hdt
+    shift = dev(s, torch.float32)
+    out = ops.inject_forward(h, shift, TD[odt], flags)
+    ref = O.inject_fwd(hn, host(shift), flags, hdt if flags else None, out_fmt=odt)
+    if odt == "fp32":
+        assert rel_err(host(out), ref) < 2e-6
+    else:
+        assert np.all(np.abs(host(out) - ref) <= np.abs(ref) * 2 * EPS[odt] + 1e-30)
+    assert rel_err(host(out), ref) < 1e-3                      # north_star's stated tolerance
+    g = dev(rng.normal(size=(n_tok, d)), TD[odt])
+    ds = torch.zeros(d, device="cuda")
+    dh = ops.inject_backward(h, g, shift, ds, True, flags)
+    o_dh, o_ds = O.inject_bwd(hn, host(shift), host(g), flags, hdt if flags else None)
+    assert rel_err(host(ds), o_ds) < 1e-4                      # stated: 1e-4 with fp32 accumulation
+    assert rel_err(host(dh), o_dh) < 1.2 * EPS[hdt]

@@ -1,0 +1,132 @@
+"""CPU-side checks of the drop-in boundary: liblicv_b200.so builds, loads and exports every symbol
+include/licv_b200.h declares; the ctypes table mirrors the header; the host-side classes keep the
+reference's API; and the product fails loudly instead of computing on the CPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from licv_vqa_b200 import (GlobalICVEncoder, ICVEncoderOutput, LMM_PRESETS,
+                           LearnableICVInterventionLMM, ModuleConfig, _abi, ops)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "licv_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(licv_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _abi.load()                      # builds with nvcc if the .so is missing
+    raw = C.CDLL(_abi.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 23
+    for name in names:
+        assert hasattr(raw, name), f"{name} is declared in licv_b200.h but not exported"
+    assert sorted(_abi.SIGNATURES) == names, "ctypes table and header disagree"
+    assert lib.licv_abi_version() == 1
+    assert b"dtype" in lib.licv_status_string(-2)
+    assert lib.licv_kd_loss_workspace_bytes(10) == 16 + 80
+    assert lib.licv_kd_loss_workspace_bytes(0) == 16
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("this box has a GPU")
+    lib = _abi.load()
+    sm, major, minor = C.c_int(), C.c_int(), C.c_int()
+    assert lib.licv_device_info(C.byref(sm), C.byref(major), C.byref(minor)) == -7  # LICV_ERR_NO_DEVICE
+    # argument checks come after the device check: every compute entry point refuses to run
+    assert lib.licv_inject_fwd(0, 0, 0, 4, 512, 1, 1, 0, 0) == -7
+    assert lib.licv_kd_loss_fwd_bwd(0, 0, 0, 0, 0, 0, 0, 0, 1.0, 1e-6, 0.0, 0, 1.0, 0, 0, 0, 8, 8, 8, 0, 0,
+                                    0) == -7
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.inject_forward(torch.zeros(2, 8), torch.zeros(8))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.kd_loss_raw(torch.zeros(2, 8), torch.zeros(2, 8))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.get_mask(torch.zeros(2, 3, dtype=torch.long), torch.zeros(2, dtype=torch.long), 0)
+
+
+def test_reference_rounding_table():
+    """Where the reference's eager chain rounds (probe-verified dtype rule)."""
+    f, dt = ops.reference_rounding(torch.bfloat16, torch.float32, autocast=False)
+    assert dt == torch.float32 and f == _abi.ROUND_NH
+    f, dt = ops.reference_rounding(torch.bfloat16, torch.float32, autocast=True)
+    assert dt == torch.float32 and f == 0
+    f, dt = ops.reference_rounding(torch.float16, torch.float16, autocast=False)
+    assert dt == torch.float16 and f == (_abi.ROUND_Y | _abi.ROUND_NH | _abi.ROUND_NY | _abi.ROUND_T)
+    f, dt = ops.reference_rounding(torch.float32, torch.float32, autocast=False)
+    assert dt == torch.float32 and f == 0
+
+
+class Tower(torch.nn.Module):
+    def __init__(self, n=3, d=8):
+        super().__init__()
+        self.layers = torch.nn.ModuleList(torch.nn.Linear(d, d) for _ in range(n))
+
+    def forward(self, x):
+        for layer in self.layers:
+            x = layer(x)
+        return x
+
+
+def test_intervention_wrapper_keeps_the_reference_api():
+    tower = Tower()
+    m = LearnableICVInterventionLMM(tower, True, -1, "layers.<LAYER_NUM>", 3)
+    assert m.intervention_layers == [0, 1, 2]
+    assert m.intervention_layer_names == ["layers.0", "layers.1", "layers.2"]
+    assert m.layer_to_icv_index == {0: 0, 1: 1, 2: 2}
+    assert m.intervention_status is True and m.intervention_enabled is True
+    assert len(m._hook_handles) == 3 and m.lmm is tower
+    m.toggle_intervention(False)
+    assert m.intervention_status is False
+    with pytest.raises(ValueError, match="boolean"):
+        m.intervention_status = 1
+    # disabled: a plain forward of the tower, no ICV needed (the teacher pass)
+    x = torch.randn(2, 8)
+    assert torch.equal(m(x=x), tower(x))
+    # enabled without an icv: the reference dies subscripting None; same exception type here
+    m.toggle_intervention(True)
+    with pytest.raises(TypeError):
+        m(x=x)
+    # enabled on CPU tensors: the injection has no CPU path and says so
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(icv=torch.zeros(1, 3, 8), x=x)
+    # a single layer / a list of layers, like the reference's _prepare_layers
+    one = LearnableICVInterventionLMM(Tower(), True, 1, "layers.<LAYER_NUM>", 3)
+    assert one.intervention_layers == [1] and one.layer_to_icv_index == {1: 0}
+    some = LearnableICVInterventionLMM(Tower(), True, [2, 0], "layers.<LAYER_NUM>", 3)
+    assert some.layer_to_icv_index == {2: 0, 0: 1}
+    with pytest.raises(LookupError):
+        LearnableICVInterventionLMM(Tower(), True, -1, "blocks.<LAYER_NUM>", 3)
+    # a second wrapper over the same tower retires the first one's hooks
+    again = LearnableICVInterventionLMM(tower, True, -1, "layers.<LAYER_NUM>", 3)
+    assert m._hook_handles == [] and len(again._hook_handles) == 3
+    off = LearnableICVInterventionLMM(Tower(), enable_intervention=False)
+    assert torch.is_tensor(off(x=x))
+
+
+def test_encoder_defaults_and_presets():
+    enc = GlobalICVEncoder(lmm_hidden_dim=16, lmm_layers=4)
+    assert enc.alpha.shape == (1, 4) and enc.icv.shape == (1, 4, 16)
+    assert float(enc.alpha.abs().max()) == 0.0 and enc.use_sigmoid is False
+    assert 0.005 < float(enc.icv.std()) < 0.02          # N(0, 0.01^2)
+    out = enc()
+    assert isinstance(out, ICVEncoderOutput) and out.in_context_feature is None
+    assert out.in_context_vector is enc.icv
+    sig = GlobalICVEncoder(16, 4, use_sigmoid=True, alpha_init_value=0.0)
+    assert torch.allclose(sig.get_alpha(), torch.full((1, 4), 0.5))
+    frozen = GlobalICVEncoder(16, 4, alpha_learnable=False, alpha_init_value=0.3)
+    assert not frozen.alpha.requires_grad and sorted(frozen.state_dict()) == ["alpha", "icv"]
+    # config/lmm/*.yaml and config/icv_module/icv_module.yaml of the reference
+    assert LMM_PRESETS["idefics-9b"].layer_format == "model.model.layers.<LAYER_NUM>"
+    assert LMM_PRESETS["idefics2-8b-base"].layer_format.endswith(".mlp")
+    cfg = ModuleConfig()
+    assert (cfg.hard_loss_weight, cfg.kl_eps, cfg.alpha_lr, cfg.icv_lr, cfg.weight_decay,
+            cfg.warm_steps, cfg.min_tmeprature) == (0.0, 1e-6, 1e-2, 1e-4, 1e-3, 0.1, 1.0)

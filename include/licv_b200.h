@@ -128,6 +128,21 @@ int licv_kd_prepare_rows(const int64_t* stu_ids, const int64_t* stu_mask_length,
                          int tea_len, int32_t* kl_tea_row, int64_t* ce_label, int32_t* counts,
                          licv_stream_t stream);
 
+/* f1 ("next" row)  the same, for teacher logits computed ONLY for the selected rows
+ *   (icv_src/icv_module.py:103-111 materialises [B, ~900, V] teacher logits to use ~32 rows):
+ *     tea_sel [B*Tq] int32 : flat teacher row of the n-th selected pair, n < N; entries n >= N
+ *                            hold 0 (a valid row), so gathering a fixed B*Tq rows of teacher
+ *                            hidden states needs no host sync
+ *     kl_tea_row           : then holds n (the row of the COMPACT teacher logits [B*Tq, V] made
+ *                            by lm_head(hidden.view(-1, d)[tea_sel])) instead of the flat row
+ *   tea_sel == NULL is licv_kd_prepare_rows. */
+int licv_kd_select_rows(const int64_t* stu_ids, const int64_t* stu_mask_length,
+                        const int64_t* stu_attention_mask, const int64_t* tea_ids,
+                        const int64_t* tea_mask_length, int64_t pad_token_id,
+                        int64_t image_token_id, int ce_variant, int batch, int stu_len,
+                        int tea_len, int32_t* kl_tea_row, int64_t* ce_label, int32_t* counts,
+                        int32_t* tea_sel, licv_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * a7+a8+a9+a10  distillation loss, forward + backward in one pass over HBM
  *   replaces VQAICVModule.calculate_kl_divergence (icv_src/icv_module.py:121-134), the HF-internal

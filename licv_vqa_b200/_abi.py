@@ -32,6 +32,8 @@ SIGNATURES = {
     "licv_get_mask": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "licv_kd_prepare_rows": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32,
                                     _vp, _vp, _vp, _vp]),
+    "licv_kd_select_rows": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32,
+                                   _vp, _vp, _vp, _vp, _vp]),
     "licv_kd_loss_workspace_bytes": (_i64, [_i64]),
     "licv_kd_loss_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32,
                                     _i32, _f32, _vp, _vp, _i64, _i32, _i64, _i64, _i32, _u32, _vp]),

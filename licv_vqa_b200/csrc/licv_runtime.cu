@@ -122,7 +122,8 @@ kd_prepare_rows_kernel(const int64_t* __restrict__ s_ids, const int64_t* __restr
                        const int64_t* __restrict__ s_att, const int64_t* __restrict__ t_ids,
                        const int64_t* __restrict__ t_len, int64_t pad, int64_t image_tok,
                        int ce_variant, int batch, int Tq, int Tt, int32_t* __restrict__ kl_tea_row,
-                       int64_t* __restrict__ ce_label, int32_t* __restrict__ counts) {
+                       int64_t* __restrict__ ce_label, int32_t* __restrict__ counts,
+                       int32_t* __restrict__ tea_sel) {
     extern __shared__ int32_t stu_by_rank[];  // [batch*Tq]: flat student row of the k-th KL row
     __shared__ int warp_tot[32];
     __shared__ int s_m;
@@ -158,10 +159,18 @@ kd_prepare_rows_kernel(const int64_t* __restrict__ s_ids, const int64_t* __restr
         }
         int tot;
         const int rk = cta_rank(sel, warp_tot, &tot);
-        if (sel && base + rk < n_stu) kl_tea_row[stu_by_rank[base + rk]] = i;
+        if (sel && base + rk < n_stu) {
+            // compact form: the student row points at the RANK of its teacher row, and tea_sel
+            // lists the selected teacher rows in that order (for a gather before lm_head)
+            kl_tea_row[stu_by_rank[base + rk]] = tea_sel ? base + rk : i;
+            if (tea_sel) tea_sel[base + rk] = i;
+        }
         base += tot;
     }
     const int n_tea = base;
+    if (tea_sel) {   // entries past the last pair: a valid row, so that a fixed-size gather is safe
+        for (int i = (n_tea < n_stu ? n_tea : n_stu) + threadIdx.x; i < ns; i += blockDim.x) tea_sel[i] = 0;
+    }
 
     // next-token labels for labels = input_ids
     int m_local = 0;
@@ -325,12 +334,30 @@ extern "C" int licv_get_mask(const int64_t* input_ids, const int64_t* mask_lengt
     return (int)cudaGetLastError();
 }
 
+extern "C" int licv_kd_select_rows(const int64_t* stu_ids, const int64_t* stu_mask_length,
+                                   const int64_t* stu_attention_mask, const int64_t* tea_ids,
+                                   const int64_t* tea_mask_length, int64_t pad_token_id,
+                                   int64_t image_token_id, int ce_variant, int batch, int stu_len,
+                                   int tea_len, int32_t* kl_tea_row, int64_t* ce_label,
+                                   int32_t* counts, int32_t* tea_sel, licv_stream_t stream);
+
 extern "C" int licv_kd_prepare_rows(const int64_t* stu_ids, const int64_t* stu_mask_length,
                                     const int64_t* stu_attention_mask, const int64_t* tea_ids,
                                     const int64_t* tea_mask_length, int64_t pad_token_id,
                                     int64_t image_token_id, int ce_variant, int batch, int stu_len,
                                     int tea_len, int32_t* kl_tea_row, int64_t* ce_label,
                                     int32_t* counts, licv_stream_t stream) {
+    return licv_kd_select_rows(stu_ids, stu_mask_length, stu_attention_mask, tea_ids,
+                               tea_mask_length, pad_token_id, image_token_id, ce_variant, batch,
+                               stu_len, tea_len, kl_tea_row, ce_label, counts, nullptr, stream);
+}
+
+extern "C" int licv_kd_select_rows(const int64_t* stu_ids, const int64_t* stu_mask_length,
+                                   const int64_t* stu_attention_mask, const int64_t* tea_ids,
+                                   const int64_t* tea_mask_length, int64_t pad_token_id,
+                                   int64_t image_token_id, int ce_variant, int batch, int stu_len,
+                                   int tea_len, int32_t* kl_tea_row, int64_t* ce_label,
+                                   int32_t* counts, int32_t* tea_sel, licv_stream_t stream) {
     if (device_info().status != LICV_OK) return device_info().status;
     if (batch <= 0 || stu_len <= 0 || tea_len <= 0 || ce_variant < 0 || ce_variant > 2)
         return LICV_ERR_BAD_ARGUMENT;
@@ -347,7 +374,7 @@ extern "C" int licv_kd_prepare_rows(const int64_t* stu_ids, const int64_t* stu_m
     }
     kd_prepare_rows_kernel<<<1, 1024, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
         stu_ids, stu_mask_length, stu_attention_mask, tea_ids, tea_mask_length, pad_token_id,
-        image_token_id, ce_variant, batch, stu_len, tea_len, kl_tea_row, ce_label, counts);
+        image_token_id, ce_variant, batch, stu_len, tea_len, kl_tea_row, ce_label, counts, tea_sel);
     return (int)cudaGetLastError();
 }
 

@@ -60,6 +60,10 @@ class ModuleConfig:
     gradient_checkpointing: bool = False  # reference enables it whenever the tower supports it
     check_row_counts: bool = False      # True: sync and raise when the two masks select != rows
     residual_dtype: str = "promote"     # see LearnableICVInterventionLMM
+    # f1: run lm_head on the teacher's SELECTED rows only (the reference materialises
+    # [B, ~900, V] teacher logits to use ~32 rows, icv_module.py:103-111).  "auto": when the tower
+    # exposes the HF get_decoder() / get_output_embeddings() pair; False: full logits
+    teacher_rows_before_lm_head: Any = "auto"
 
 
 @dataclass
@@ -203,16 +207,20 @@ class VQAICVModule(nn.Module):
                                       temperature=self._temperature_value, only_hard_loss=True)
             return {"loss": total}, icv_encoder_output
 
-        with torch.no_grad():
-            self.icv_model.toggle_intervention(False)
-            ice_logits = self.icv_model(**inputs)["logits"]
-        if ice_logits.dtype != icv_logits.dtype:
-            ice_logits = ice_logits.to(icv_logits.dtype)
-
-        kl_tea_row, ce_label, counts = ops.kd_prepare_rows(
+        compact = self._teacher_head_parts() is not None
+        prep = ops.kd_prepare_rows(
             stu_ids, query_x_length, inputs[ids_name], in_context_length, pad_id,
             query_inputs.get("attention_mask"), self._ce_variant(),
-            _get(cfg, "image_token_id", -1), want_ce=want_ce)
+            _get(cfg, "image_token_id", -1), want_ce=want_ce, compact_teacher=compact)
+        kl_tea_row, ce_label, counts = prep[:3]
+        with torch.no_grad():
+            self.icv_model.toggle_intervention(False)
+            if compact:
+                ice_logits = self._teacher_logits_of_rows(inputs, prep[3])
+            else:
+                ice_logits = self.icv_model(**inputs)["logits"]
+        if ice_logits.dtype != icv_logits.dtype:
+            ice_logits = ice_logits.to(icv_logits.dtype)
         if _get(cfg, "check_row_counts", False):
             n_s, _, n_t, _ = counts.tolist()
             if n_s != n_t:
@@ -227,6 +235,40 @@ class VQAICVModule(nn.Module):
             loss_dict["ce_loss"] = ce
         loss_dict["loss"] = total
         return loss_dict, icv_encoder_output
+
+    # ------------------------------------------------------------------ f1: teacher rows only
+    def _teacher_head_parts(self):
+        """(decoder, lm_head) when the teacher's logits can be restricted to the selected rows."""
+        want = _get(self.module_cfg, "teacher_rows_before_lm_head", "auto")
+        if want is False:
+            return None
+        model = getattr(self.interface, "model", None)
+        dec = getattr(model, "get_decoder", None)
+        head = getattr(model, "get_output_embeddings", None)
+        try:
+            dec, head = (dec() if dec else None), (head() if head else None)
+        except Exception:
+            dec = head = None
+        if dec is None or head is None or dec is model:
+            if want is True:
+                raise RuntimeError("teacher_rows_before_lm_head=True needs a tower with "
+                                   "get_decoder() and get_output_embeddings()")
+            return None
+        return dec, head
+
+    def _teacher_logits_of_rows(self, inputs, tea_sel):
+        """lm_head over the gathered hidden rows: [B*Tq, V] compact teacher logits (hooks are off:
+        the decoder's layers carry them, disabled by toggle_intervention(False))."""
+        dec, head = self._teacher_head_parts()
+        previous = self.icv_model._active
+        self.icv_model._active = None          # what LearnableICVInterventionLMM._run does when off
+        try:
+            hidden = dec(**{k: v for k, v in inputs.items() if k != "labels"})
+        finally:
+            self.icv_model._active = previous
+        hidden = hidden[0] if isinstance(hidden, tuple) else hidden.last_hidden_state
+        rows = hidden.reshape(-1, hidden.shape[-1]).index_select(0, tea_sel.long())
+        return head(rows)
 
     def calculate_kl_divergence(self, stu_logits, tea_logits):
         """T^2 * mean_rows sum_v p (log(p+eps) - log(q+eps)) (icv_module.py:121-134).

@@ -225,10 +225,13 @@ CE_VARIANTS = {"idefics": 0, "idefics2": 1, "causal_lm": 2}
 
 def kd_prepare_rows(stu_ids, stu_mask_length, tea_ids, tea_mask_length, pad_token_id,
                     stu_attention_mask=None, ce_variant="idefics", image_token_id=-1,
-                    want_ce=True):
+                    want_ce=True, compact_teacher=False):
     """Row pairing and next-token labels without gathers or host syncs.
 
     -> (kl_tea_row int32 [B*Tq], ce_label int64 [B*Tq] or None, counts int32 [4] = N, M, N_tea, 0)
+    With ``compact_teacher`` a fourth value ``tea_sel`` int32 [B*Tq] is returned (flat teacher row
+    of the n-th pair, 0 beyond the last) and ``kl_tea_row`` indexes the compact teacher logits
+    ``lm_head(hidden.view(-1, d)[tea_sel])`` instead of the full [B*Tt, V] ones.
     """
     _need_cuda(stu_ids, stu_mask_length, tea_ids, tea_mask_length, stu_attention_mask)
     B, Tq = stu_ids.shape
@@ -244,11 +247,14 @@ def kd_prepare_rows(stu_ids, stu_mask_length, tea_ids, tea_mask_length, pad_toke
     kl_tea_row = torch.empty(B * Tq, dtype=torch.int32, device=dev)
     ce_label = torch.empty(B * Tq, dtype=torch.int64, device=dev) if want_ce else None
     counts = torch.empty(4, dtype=torch.int32, device=dev)
-    _abi.check(_abi.load().licv_kd_prepare_rows(
+    tea_sel = torch.empty(B * Tq, dtype=torch.int32, device=dev) if compact_teacher else None
+    _abi.check(_abi.load().licv_kd_select_rows(
         s_ids.data_ptr(), s_len.data_ptr(), _ptr(s_att), t_ids.data_ptr(), t_len.data_ptr(),
         int(pad_token_id), int(image_token_id), CE_VARIANTS[ce_variant], B, Tq, Tt,
-        kl_tea_row.data_ptr(), _ptr(ce_label), counts.data_ptr(), _stream()),
-        "licv_kd_prepare_rows")
+        kl_tea_row.data_ptr(), _ptr(ce_label), counts.data_ptr(), _ptr(tea_sel), _stream()),
+        "licv_kd_select_rows")
+    if compact_teacher:
+        return kl_tea_row, ce_label, counts, tea_sel
     return kl_tea_row, ce_label, counts
 
 

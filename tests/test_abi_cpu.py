@@ -130,3 +130,56 @@ def test_encoder_defaults_and_presets():
     cfg = ModuleConfig()
     assert (cfg.hard_loss_weight, cfg.kl_eps, cfg.alpha_lr, cfg.icv_lr, cfg.weight_decay,
             cfg.warm_steps, cfg.min_tmeprature) == (0.0, 1e-6, 1e-2, 1e-4, 1e-3, 0.1, 1.0)
+
+
+def test_checkpoint_wire_format_round_trip(tmp_path):
+    """f3: the dict the reference writes as icv_cpk.pth (train.py:97-106) and inference.py:95-100
+    reads - keys icv_encoder.icv / icv_encoder.alpha / use_sigmoid / lmm_args."""
+    from licv_vqa_b200 import LMMConfig, VQAICVModule, load_icv_for_inference
+    from licv_vqa_b200.icv_module import ICVEncoderConfig
+
+    class Iface(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = Tower(3, 8)
+            self.tokenizer = type("Tok", (), {"pad_token_id": 0})()
+            self.input_ids_field_name = "input_ids"
+
+        def forward(self, **kw):
+            return self.model(**kw)
+
+    cfg = ModuleConfig(icv_encoder=ICVEncoderConfig(use_sigmoid=True, alpha_init_value=0.2))
+    lmm = LMMConfig("toy", 3, "model.layers.<LAYER_NUM>", -1, 8)
+    mod = VQAICVModule(Iface(), cfg, lmm)
+    assert all(not p.requires_grad for p in mod.interface.parameters())     # frozen tower
+    assert sorted(k for k, p in mod.named_parameters() if p.requires_grad) == \
+        ["icv_encoder.alpha", "icv_encoder.icv"]
+    with torch.no_grad():
+        mod.icv_encoder.icv.normal_()
+    path = tmp_path / "icv_cpk.pth"
+    mod.save_icv_checkpoint(path)
+    ck = torch.load(path, map_location="cpu")
+    assert {"icv_encoder.icv", "icv_encoder.alpha", "use_sigmoid", "lmm_args"} <= set(ck)
+    assert ck["lmm_args"]["layer_format"] == "model.layers.<LAYER_NUM>"
+    assert ck["lmm_args"]["total_layers"] == 3 and ck["lmm_args"]["intervention_layer"] == -1
+    # what inference.py does with it: alpha through the sigmoid when the checkpoint says so
+    icv, alpha, lmm_args = load_icv_for_inference(path, "cpu")
+    assert torch.equal(icv, mod.icv_encoder.icv.detach())
+    assert torch.allclose(alpha, torch.sigmoid(mod.icv_encoder.alpha.detach()))
+    assert lmm_args["hidden_size"] == 8
+    # and back into a fresh module
+    other = VQAICVModule(Iface(), cfg, lmm)
+    other.load_icv_checkpoint(path)
+    assert torch.equal(other.icv_encoder.icv, mod.icv_encoder.icv)
+    # temperature schedule on the host mirror (icv_module.py:54-69,150-158)
+    dec = VQAICVModule(Iface(), ModuleConfig(init_temperature=4.0, decay_ratio=0.5, decay_per_step=2,
+                                             min_tmeprature=1.5), lmm)
+    assert dec.setup_temperature_decay(100) == 2
+    seen = []
+    for step in range(7):
+        dec.global_step = step
+        dec.decay_temperature()
+        seen.append(dec._temperature_value)
+    assert seen == [4.0, 4.0, 2.0, 2.0, 1.5, 1.5, 1.5] and float(dec.temperature) == 1.5
+    with pytest.raises(NotImplementedError):
+        VQAICVModule(Iface(), ModuleConfig(learnable_t=True), lmm)

@@ -91,6 +91,16 @@ def test_prepare_rows_vs_oracle(ops, variant, B, Tq, Tc):
     assert np.array_equal(lab.cpu().numpy(), want_lab)
     c = counts.cpu().numpy()
     assert c[0] == (want_ktr >= 0).sum() and c[1] == (want_lab != -100).sum() and c[2] == c[0]
+    # compact form (f1): kl_tea_row holds ranks, tea_sel the flat teacher rows in rank order
+    k3, _, c3, sel = ops.kd_prepare_rows(
+        torch.tensor(s_ids).cuda(), torch.tensor(qx).cuda(), torch.tensor(t_ids).cuda(),
+        torch.tensor(icl).cuda(), 0, torch.tensor(s_att).cuda(), variant, img, compact_teacher=True)
+    k3, sel = k3.cpu().numpy(), sel.cpu().numpy()
+    n = int(c3[0])
+    assert sel.shape == (B * Tq,) and np.array_equal(sel[:n], np.sort(want_ktr[want_ktr >= 0]))
+    assert not sel[n:].any()
+    assert np.array_equal(k3 >= 0, want_ktr >= 0)
+    assert np.array_equal(sel[k3[k3 >= 0]], want_ktr[want_ktr >= 0])
     # no CE wanted: labels are not produced
     ktr2, lab2, _ = ops.kd_prepare_rows(
         torch.tensor(s_ids).cuda(), torch.tensor(qx).cuda(), torch.tensor(t_ids).cuda(),

@@ -55,13 +55,15 @@ def tower():
     return model.cuda()
 
 
+@pytest.mark.parametrize("rows_first", [True, False])
 @pytest.mark.parametrize("name", [str(n) for n in G["names"]])
-def test_module_matches_reference_end_to_end(tower, name):
+def test_module_matches_reference_end_to_end(tower, name, rows_first):
     from licv_vqa_b200 import LMMConfig, ModuleConfig, VQAICVModule
     from licv_vqa_b200.icv_module import ICVEncoderConfig
     sig, hlw, T = G[f"{name}/cfg"]
     cfg = ModuleConfig(hard_loss_weight=float(hlw), init_temperature=float(T), kl_eps=1e-6,
                        ce_variant="causal_lm",   # what the fixture's transformers computes
+                       teacher_rows_before_lm_head=rows_first,   # f1: lm_head on selected rows
                        icv_encoder=ICVEncoderConfig(use_sigmoid=bool(sig), alpha_init_value=0.1))
     lmm = LMMConfig("tiny-llama", 2, "model.model.layers.<LAYER_NUM>", -1, 512)
     mod = VQAICVModule(Interface(tower), cfg, lmm).cuda()

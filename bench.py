@@ -197,6 +197,20 @@ class HotPath:
         self.flags = (_abi.ROUND_Y | _abi.ROUND_NH | _abi.ROUND_NY | _abi.ROUND_T
                       if dtype != torch.float32 else 0)
         self.step_no = 0
+        # N > 1: the gradient exchange is fused with the optimizer step over NVLink peer memory
+        # (csrc/licv_dp.cu); LICV_DP_EXCHANGE=nccl selects all_reduce + optimizer kernels instead
+        self.peer, self.peer_note = None, ""
+        if world > 1 and os.environ.get("LICV_DP_EXCHANGE", "p2p") != "nccl":
+            from licv_vqa_b200.dp import PeerExchange
+            ok = torch.ones(1, device=device)
+            try:
+                self.peer = PeerExchange(self.grad.numel())
+            except Exception as exc:       # peers not mappable: every rank must take the same path
+                self.peer_note = f" (p2p unavailable: {exc})"
+                ok.zero_()
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+            if float(ok) == 0.0:
+                self.peer = None
 
     def _chk(self, rc, what):
         if rc != 0:
@@ -237,8 +251,15 @@ class HotPath:
                                          g + 4 * self.n_vec, L, d, int(CFG["use_sigmoid"]), st),
                   "icv_scale_bwd")
         if self.world > 1 and allreduce:
-            # logged scalars ride in the tail of the same flat buffer (one collective per step)
+            # logged scalars ride in the tail of the same flat buffer (one exchange per step)
             self.grad[self.n_vec + self.n_alpha:self.n_vec + self.n_alpha + 3].copy_(self.losses[:3])
+            if self.peer is not None:
+                self.step_no += 1
+                self._chk(lib.licv_dp_allreduce_adamw(
+                    self.peer.comm, p, g, self.m.data_ptr(), self.v.data_ptr(), self.n_vec,
+                    self.n_alpha, 4, 1e-4, 1e-2, 0.9, 0.999, 1e-8, 1e-3, self.step_no, 1.0,
+                    self.norm.data_ptr(), self.opt_ws.data_ptr(), st), "dp_allreduce_adamw")
+                return
             torch.distributed.all_reduce(self.grad)
         self.step_no += 1
         self._chk(lib.licv_adamw_step(p, g, self.m.data_ptr(), self.v.data_ptr(), self.n_vec,
@@ -659,6 +680,9 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": CFG["dtype"] + " (fp32 accumulate)",
         "data": "synthetic",
         "config": dict(CFG, global_batch=CFG["batch_per_gpu"] * world, parallelism=f"dp{world}",
+                       grad_exchange=("none (1 GPU)" if world == 1 else
+                                      "fused p2p exchange + AdamW over NVLink peer memory"
+                                      if hp.peer is not None else "nccl all_reduce" + hp.peer_note),
                        cuda_graph=graph is not None,
                        flush="inputs of one step (~290 MB, a distinct buffer per layer) exceed L2"),
         "roofline": roofline, "clocks": clocks.summary(),

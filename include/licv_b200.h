@@ -192,6 +192,33 @@ int licv_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_
                     licv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * e  data-parallel gradient exchange fused with the optimizer step, over NVLink peer memory
+ *   replaces Lightning DDP's NCCL all-reduce of icv_encoder.*.grad, the sync_dist collective of
+ *   the logged scalars (icv_src/icv_module.py:163) and the optimizer step (config/trainer/
+ *   ddp.yaml:5,7; icv_module.py:171-209) for one process per GPU on one NVSwitch node.
+ *   Set-up (once): every rank allocates a region (licv_dp_region_alloc returns a 64-byte CUDA IPC
+ *   handle), the ranks exchange the handles (any host channel), licv_dp_comm_create maps the
+ *   peers.  Per optimizer step: licv_dp_allreduce_adamw - `grad` [n_vec + n_alpha + n_extra,
+ *   rounded up to 4 floats] holds the local gradient (+ n_extra logged scalars) on entry and the
+ *   SUM over ranks on return (summed in rank order: bit-identical on every rank); the parameters
+ *   are updated with the mean gradient (clip at max_grad_norm, AdamW).  Two launches, no host
+ *   synchronisation, replayable from a CUDA graph (the step counter lives in device memory).
+ *   world == 1 degenerates to licv_adamw_step.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct licv_dp_comm licv_dp_comm;
+int64_t licv_dp_region_bytes(int64_t n_floats);
+int licv_dp_region_alloc(int64_t n_floats, void** region, void* ipc_handle_64);
+int licv_dp_comm_create(licv_dp_comm** out, int rank, int world, void* region,
+                        const void* all_handles /* world x 64 bytes, rank order */, int64_t n_floats);
+int licv_dp_comm_destroy(licv_dp_comm* c);
+int licv_dp_comm_error(licv_dp_comm* c); /* 1 if a wait for a peer ever timed out */
+int licv_dp_allreduce_adamw(licv_dp_comm* c, float* param, float* grad, float* exp_avg,
+                            float* exp_avg_sq, int64_t n_vec, int64_t n_alpha, int64_t n_extra,
+                            float lr_vec, float lr_alpha, float beta1, float beta2, float eps,
+                            float weight_decay, int64_t step, float max_grad_norm, float* norm_out,
+                            void* workspace /* >= 16 B, zeroed */, licv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a host-side plugin of the reference would call): inputs and
  * outputs live in HOST memory.  Pinned / registered buffers are read and written by the kernels
  * directly over the host link (zero-copy: both directions busy inside one kernel, nothing staged

@@ -228,12 +228,27 @@ struct AdamArgs {
     float* norm_out;
     float* acc;            // workspace[0]: sum of squares
     unsigned* ticket;      // workspace[1]
+    const float* partials; // or: n_partials sums of squares to be added in index order
+    int n_partials;
 };
 
 __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
     // every CTA reads the norm before taking a ticket; the last ticket holder clears the workspace
     float coef = a.prescale;
-    const float norm = sqrtf(*reinterpret_cast<volatile float*>(a.acc));
+    float sumsq;
+    if (a.partials != nullptr) {   // fixed-order sum: the same bits in every CTA and on every rank
+        __shared__ float s_sumsq;
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int i = 0; i < a.n_partials; ++i) t += a.partials[i];
+            s_sumsq = t;
+        }
+        __syncthreads();
+        sumsq = s_sumsq;
+    } else {
+        sumsq = *reinterpret_cast<volatile float*>(a.acc);
+    }
+    const float norm = sqrtf(sumsq);
     if (a.max_norm > 0.f) {
         const float c = a.max_norm / (norm + 1e-6f);   // torch.nn.utils.clip_grad_norm_
         coef *= fminf(c, 1.0f);
@@ -378,6 +393,33 @@ extern "C" int licv_kd_select_rows(const int64_t* stu_ids, const int64_t* stu_ma
     return (int)cudaGetLastError();
 }
 
+namespace licv {
+// AdamW kernel alone; the squared gradient norm (of grad * grad_prescale) is already in workspace[0]
+int launch_adamw_after_norm(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                            int64_t n_vec, int64_t n_alpha, float lr_vec, float lr_alpha, float beta1,
+                            float beta2, float eps, float weight_decay, int64_t step,
+                            float grad_prescale, float max_grad_norm, float* norm_out,
+                            void* workspace, const float* norm_partials, int n_partials,
+                            cudaStream_t st) {
+    const int64_t n = n_vec + n_alpha;
+    AdamArgs a;
+    a.partials = norm_partials;
+    a.n_partials = n_partials;
+    a.p = param; a.g = grad; a.m = exp_avg; a.v = exp_avg_sq;
+    a.n_vec = n_vec; a.n_alpha = n_alpha;
+    a.lr_vec = lr_vec; a.lr_alpha = lr_alpha; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+    a.wd = weight_decay; a.prescale = grad_prescale; a.max_norm = max_grad_norm;
+    a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    a.norm_out = norm_out;
+    a.acc = static_cast<float*>(workspace);
+    a.ticket = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + 4);
+    const int grid = (int)((n + 1023) / 1024 < 148 ? (n + 1023) / 1024 : 148);
+    adamw_kernel<<<grid, 256, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}
+}  // namespace licv
+
 extern "C" int licv_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                                int64_t n_vec, int64_t n_alpha, float lr_vec, float lr_alpha,
                                float beta1, float beta2, float eps, float weight_decay, int64_t step,
@@ -389,18 +431,9 @@ extern "C" int licv_adamw_step(float* param, const float* grad, float* exp_avg, 
     if (n == 0) return LICV_OK;
     if (!param || !grad || !exp_avg || !exp_avg_sq || !workspace) return LICV_ERR_NULL_POINTER;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    AdamArgs a;
-    a.p = param; a.g = grad; a.m = exp_avg; a.v = exp_avg_sq;
-    a.n_vec = n_vec; a.n_alpha = n_alpha;
-    a.lr_vec = lr_vec; a.lr_alpha = lr_alpha; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
-    a.wd = weight_decay; a.prescale = grad_prescale; a.max_norm = max_grad_norm;
-    a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
-    a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
-    a.norm_out = norm_out;
-    a.acc = static_cast<float*>(workspace);
-    a.ticket = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + 4);
     const int grid = (int)((n + 1023) / 1024 < 148 ? (n + 1023) / 1024 : 148);
-    sumsq_kernel<<<grid, 256, 0, st>>>(grad, n, grad_prescale, a.acc);
-    adamw_kernel<<<grid, 256, 0, st>>>(a);
-    return (int)cudaGetLastError();
+    sumsq_kernel<<<grid, 256, 0, st>>>(grad, n, grad_prescale, static_cast<float*>(workspace));
+    return launch_adamw_after_norm(param, grad, exp_avg, exp_avg_sq, n_vec, n_alpha, lr_vec, lr_alpha,
+                                   beta1, beta2, eps, weight_decay, step, grad_prescale,
+                                   max_grad_norm, norm_out, workspace, nullptr, 0, st);
 }

@@ -75,7 +75,8 @@ class FlatICVState:
         n = self.n_vec + self.n_alpha
         dev = icv.device
         self.param = torch.empty(n, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(n + N_SCALARS, dtype=torch.float32, device=dev)
+        # rounded up to whole 16-byte vectors (the peer-memory exchange moves float4s)
+        self.grad = torch.zeros((n + N_SCALARS + 3) // 4 * 4, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         with torch.no_grad():
@@ -111,6 +112,58 @@ class FlatICVState:
         self.rebind()
 
 
+class PeerExchange:
+    """The fused gradient exchange + optimizer step over NVLink peer memory (csrc/licv_dp.cu).
+
+    One instance per rank; `world` processes on one node, one GPU each.  Set-up allocates this
+    rank's exchange region in the library (cudaMalloc + CUDA IPC handle), all-gathers the 64-byte
+    handles over the existing process group, and maps the peers.  After that a step is two kernel
+    launches and no collective call."""
+
+    def __init__(self, n_floats: int, group=None):
+        import ctypes as C
+
+        from . import _abi
+        self._abi, self._C = _abi, C
+        self.lib = _abi.load()
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n = int(n_floats)
+        region, handle = C.c_void_p(), C.create_string_buffer(64)
+        _abi.check(self.lib.licv_dp_region_alloc(self.n, C.byref(region), handle), "licv_dp_region_alloc")
+        handles = handle.raw
+        if self.world > 1:
+            mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).cuda()
+            every = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(every, mine, group=group)
+            handles = b"".join(bytes(t.cpu().tolist()) for t in every)
+        self._handles = C.create_string_buffer(handles, len(handles))
+        comm = C.c_void_p()
+        _abi.check(self.lib.licv_dp_comm_create(C.byref(comm), self.rank, self.world, region,
+                                                self._handles, self.n), "licv_dp_comm_create")
+        self.comm = comm
+        if self.world > 1:
+            dist.barrier(group=group)     # every rank has mapped every region before the first step
+
+    def step(self, param, grad, exp_avg, exp_avg_sq, n_vec, n_alpha, n_extra, lr_vec, lr_alpha,
+             betas, eps, weight_decay, step, max_grad_norm, norm_out, workspace):
+        self._abi.check(self.lib.licv_dp_allreduce_adamw(
+            self.comm, param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+            int(n_vec), int(n_alpha), int(n_extra), float(lr_vec), float(lr_alpha), float(betas[0]),
+            float(betas[1]), float(eps), float(weight_decay), int(step), float(max_grad_norm),
+            norm_out.data_ptr(), workspace.data_ptr(), torch.cuda.current_stream().cuda_stream),
+            "licv_dp_allreduce_adamw")
+
+    def timed_out(self) -> bool:
+        return self.lib.licv_dp_comm_error(self.comm) == 1
+
+    def close(self):
+        if getattr(self, "comm", None) is not None and self.comm:
+            self.lib.licv_dp_comm_destroy(self.comm)
+            self.comm = None
+
+
 class ICVDataParallelOptimizer:
     """all-reduce + clip + AdamW + cosine warm-up for the ICV parameters of one rank.
 
@@ -124,7 +177,10 @@ class ICVDataParallelOptimizer:
 
     def __init__(self, encoder: torch.nn.Module, module_cfg=None, total_steps: int = 1,
                  max_grad_norm: float = 1.0, process_group=None, betas=(0.9, 0.999),
-                 eps: float = 1e-8):
+                 eps: float = 1e-8, exchange: str = "auto"):
+        """``exchange``: "p2p" = fused exchange + optimizer over NVLink peer memory (one node),
+        "nccl" = `all_reduce` then the optimizer kernels, "auto" = p2p for CUDA parameters in a
+        multi-rank group when the peers can be mapped, else nccl."""
         def get(name, default):
             if module_cfg is None:
                 return default
@@ -146,6 +202,16 @@ class ICVDataParallelOptimizer:
         dev = self.state.param.device
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self._ws = torch.zeros(16, dtype=torch.uint8, device=dev)
+        self.peer = None
+        if exchange not in ("auto", "p2p", "nccl"):
+            raise ValueError("exchange must be 'auto', 'p2p' or 'nccl'")
+        if exchange != "nccl" and dev.type == "cuda" and self.world_size > 1:
+            try:
+                self.peer = PeerExchange(self.state.grad.numel(), process_group)
+            except Exception:
+                if exchange == "p2p":
+                    raise
+                self.peer = None
 
     # ------------------------------------------------------------------ distributed plumbing
     @property
@@ -157,9 +223,8 @@ class ICVDataParallelOptimizer:
     def zero_grad(self):
         self.state.zero_grad()
 
-    def all_reduce_gradients(self, logged: Optional[Dict[str, torch.Tensor]] = None) -> None:
-        """SUM over ranks of [grads | logged scalars], in place, one collective.  The division by
-        world size is folded into the optimizer kernel (`grad_prescale`) and into `synced_logs`."""
+    def stage_logged(self, logged: Optional[Dict[str, torch.Tensor]] = None) -> None:
+        """The logged scalars ride in the tail of the flat gradient buffer."""
         st = self.state
         st.rebind()
         if logged:
@@ -167,6 +232,12 @@ class ICVDataParallelOptimizer:
             for i, key in enumerate(("kl_loss", "ce_loss", "loss")):
                 if key in logged and logged[key] is not None:
                     sc[i].copy_(logged[key].detach().to(sc.dtype).reshape(()))
+
+    def all_reduce_gradients(self, logged: Optional[Dict[str, torch.Tensor]] = None) -> None:
+        """SUM over ranks of [grads | logged scalars], in place, one collective.  The division by
+        world size is folded into the optimizer kernel (`grad_prescale`) and into `synced_logs`."""
+        st = self.state
+        self.stage_logged(logged)
         if self.world_size > 1:
             dist.all_reduce(st.grad, op=dist.ReduceOp.SUM, group=self.group)
 
@@ -186,8 +257,20 @@ class ICVDataParallelOptimizer:
             raise RuntimeError("ICVDataParallelOptimizer.step runs the fused sm_100a optimizer "
                                "kernel: the ICV parameters must live on a B200 (no CPU optimizer)")
         from . import ops
-        self.all_reduce_gradients(logged)
         lr_vec, lr_alpha = self.current_lrs()          # scheduler value BEFORE this step's update
+        if self.peer is not None:
+            # ONE fused exchange + optimizer step over peer memory: no collective call
+            self.stage_logged(logged)
+            self.step_no += 1
+            self.peer.step(st.param, st.grad, st.exp_avg, st.exp_avg_sq, st.n_vec,
+                           st.n_alpha if st.alpha_learnable else 0,
+                           st.grad.numel() - st.n_vec - (st.n_alpha if st.alpha_learnable else 0),
+                           lr_vec, lr_alpha, self.betas, self.eps, self.weight_decay, self.step_no,
+                           self.max_grad_norm, self.grad_norm, self._ws)
+            logs = {k: v.clone() for k, v in self.synced_logs().items()} if logged else {}
+            self.zero_grad()
+            return logs
+        self.all_reduce_gradients(logged)
         self.step_no += 1
         ops.adamw_step(st.param, st.grad, st.exp_avg, st.exp_avg_sq, st.n_vec,
                        st.n_alpha if st.alpha_learnable else 0, lr_vec, lr_alpha, self.step_no,

@@ -74,7 +74,7 @@ def test_flat_buffer_allreduce_world2(tmp_path):
     want_v = sum(2 * _rank_grads(r)[0] for r in range(world)).reshape(-1).numpy()
     want_a = sum(2 * _rank_grads(r)[1] for r in range(world)).reshape(-1).numpy()
     n = L * D + L
-    assert g0.shape == (n + N_SCALARS,)
+    assert g0.shape == ((n + N_SCALARS + 3) // 4 * 4,)
     np.testing.assert_allclose(g0[:L * D], want_v, rtol=1e-6)
     np.testing.assert_allclose(g0[L * D:n], want_a, rtol=1e-6)
     # scalars: SUM in the buffer, mean in synced_logs (log_dict(sync_dist=True) semantics)

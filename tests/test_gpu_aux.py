@@ -257,3 +257,35 @@ def test_no_cpu_path(ops):
         ops.inject_forward(torch.zeros(2, 8), torch.zeros(8))
     with pytest.raises(RuntimeError, match="no CPU path"):
         ops.kd_loss_raw(torch.zeros(2, 8), torch.zeros(2, 8))
+
+
+def test_peer_exchange_world1_equals_adamw_step(ops):
+    """csrc/licv_dp.cu with a single rank: exchange + optimizer == licv_adamw_step (the multi-rank
+    protocol is checked under torchrun by tools/dp_p2p_check.py)."""
+    from licv_vqa_b200.dp import PeerExchange
+    n_vec, n_alpha, n_extra = 4096 * 3, 3, 5
+    n = n_vec + n_alpha + n_extra
+    npad = (n + 3) // 4 * 4
+    g = torch.Generator(device="cuda").manual_seed(5)
+    p0 = torch.randn(n_vec + n_alpha, device="cuda", generator=g)
+    grad0 = torch.zeros(npad, device="cuda")
+    grad0[:n] = torch.randn(n, device="cuda", generator=g)
+    pa, pb = p0.clone(), p0.clone()
+    ma, va, mb, vb = (torch.zeros_like(p0) for _ in range(4))
+    na, nb = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    wa, wb = torch.zeros(16, dtype=torch.uint8, device="cuda"), torch.zeros(16, dtype=torch.uint8, device="cuda")
+    ex = PeerExchange(npad)
+    try:
+        for step in (1, 2, 3):
+            ga = grad0.clone() * step
+            gb = ga.clone()
+            ex.step(pa, ga, ma, va, n_vec, n_alpha, npad - n_vec - n_alpha, 1e-3, 1e-2, (0.9, 0.999), 1e-8,
+                    1e-3, step, 1.0, na, wa)
+            ops.adamw_step(pb, gb, mb, vb, n_vec, n_alpha, 1e-3, 1e-2, step, grad_prescale=1.0,
+                           max_grad_norm=1.0, norm_out=nb, workspace=wb)
+            assert torch.equal(ga, gb)                       # the sum over one rank is the gradient
+            assert torch.allclose(na, nb, rtol=1e-5)
+            assert rel_err(host(pa), host(pb)) < 1e-6
+        assert not ex.timed_out()
+    finally:
+        ex.close()

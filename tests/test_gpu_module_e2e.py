@@ -108,3 +108,70 @@ def test_generate_with_icv_runs_and_changes_output(tower):
         b = m.generate(input_ids=ids, max_new_tokens=4, do_sample=False)
     assert a.shape == b.shape == (2, 12)
     assert not torch.equal(a, b)
+
+
+@pytest.mark.parametrize("layer_format,layers", [
+    ("model.model.layers.<LAYER_NUM>.mlp", -1),       # idefics2's hook point: MLP output, pre-residual
+    ("model.model.layers.<LAYER_NUM>", [1]),          # a single hooked layer
+    ("model.model.layers.<LAYER_NUM>.mlp", [1, 0]),   # a list, in the caller's order
+])
+def test_hook_points_match_eager_torch_hooks(tower, layer_format, layers):
+    """BASELINE configs[2] semantics (config/lmm/idefics2-8B-base.yaml:8): the same module against
+    plain torch forward hooks running the reference's five-op chain + autograd on the same tower
+    (fp32 on both sides), for hook points / layer subsets the golden file does not hold."""
+    from licv_vqa_b200 import LMMConfig, ModuleConfig, VQAICVModule
+    from licv_vqa_b200.icv_module import ICVEncoderConfig
+    dev = "cuda"
+    n_hook = 2 if layers == -1 else len(layers)
+    cfg = ModuleConfig(hard_loss_weight=0.5, kl_eps=1e-6, ce_variant="causal_lm",
+                       icv_encoder=ICVEncoderConfig(use_sigmoid=True, alpha_init_value=0.3))
+    mod = VQAICVModule(Interface(tower), cfg, LMMConfig("tiny", 2, layer_format, layers, 512)).cuda()
+    gen = torch.Generator().manual_seed(11)
+    vec = torch.randn(1, n_hook, 512, generator=gen) * 0.5
+    with torch.no_grad():
+        mod.icv_encoder.icv.copy_(vec)
+    q = {"input_ids": torch.tensor(G["q_ids"]).to(dev), "attention_mask": torch.tensor(G["q_att"]).to(dev)}
+    t = {"input_ids": torch.tensor(G["t_ids"]).to(dev), "attention_mask": torch.tensor(G["t_att"]).to(dev)}
+    qxl = torch.tensor(G["query_x_length"]).to(dev)
+    icl = torch.tensor(G["in_context_length"]).to(dev)
+    loss_dict, _ = mod(q, t, qxl, icl)
+    loss_dict["loss"].backward()
+    got = (float(loss_dict["kl_loss"]), float(loss_dict["ce_loss"]),
+           mod.icv_encoder.icv.grad.clone(), mod.icv_encoder.alpha.grad.clone())
+    mod.icv_model.remove_hooks()
+
+    # the reference's chain as plain torch hooks (icv_intervention.py:61-86, icv_module.py:84-134)
+    alpha = torch.full((1, n_hook), 0.3, device=dev, requires_grad=True)
+    icv_p = vec.to(dev).requires_grad_(True)
+    ids = list(range(2)) if layers == -1 else layers
+    names = [layer_format.replace("<LAYER_NUM>", str(i)) for i in ids]
+    named = dict(Interface(tower).named_modules())
+    state = {"icv": None}
+    handles = []
+    for k, name in enumerate(names):
+        def fn(_m, _a, out, k=k):
+            if state["icv"] is None:
+                return None
+            h = out[0] if isinstance(out, tuple) else out
+            y = h + state["icv"][:, k].unsqueeze(1)
+            y = y / y.norm(dim=-1, keepdim=True) * h.norm(dim=-1, keepdim=True)
+            return (y,) + tuple(out[1:]) if isinstance(out, tuple) else y
+        handles.append(named[name].register_forward_hook(fn))
+    try:
+        state["icv"] = torch.sigmoid(alpha).unsqueeze(-1) * icv_p
+        so = tower(**q, labels=q["input_ids"])
+        state["icv"] = None
+        with torch.no_grad():
+            tl = tower(**t).logits
+        mq = (torch.arange(q["input_ids"].shape[1], device=dev)[None] >= qxl[:, None]) & (q["input_ids"] != 0)
+        mt = (torch.arange(t["input_ids"].shape[1], device=dev)[None] >= icl[:, None]) & (t["input_ids"] != 0)
+        p, qq = torch.softmax(tl[mt], 1), torch.softmax(so.logits[mq], 1)
+        kl = (p * (torch.log(p + 1e-6) - torch.log(qq + 1e-6))).sum(1).mean()
+        (kl + 0.5 * so.loss).backward()
+    finally:
+        for h in handles:
+            h.remove()
+    assert abs(got[0] - float(kl)) <= 1e-4 * abs(float(kl))
+    assert abs(got[1] - float(so.loss)) <= 1e-4 * abs(float(so.loss))
+    assert rel_err(got[2].cpu().numpy(), icv_p.grad.cpu().numpy()) < 1e-4
+    assert rel_err(got[3].cpu().numpy(), alpha.grad.cpu().numpy()) < 1e-4

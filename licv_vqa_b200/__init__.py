@@ -7,12 +7,13 @@ GPU only - there is no CPU path and no fallback.
 """
 from .icv_encoder import BaseICVEncoder, GlobalICVEncoder, ICVEncoderOutput
 from .icv_model import LearnableICVInterventionLMM
+from .collate import check_batch_contract, collate_token_ids
 from .icv_module import (ICVEncoderConfig, LMM_PRESETS, LMMConfig, ModuleConfig, VQAICVModule,
                          load_icv_for_inference)
 
 __all__ = [
     "BaseICVEncoder", "GlobalICVEncoder", "ICVEncoderOutput", "LearnableICVInterventionLMM",
     "VQAICVModule", "ModuleConfig", "LMMConfig", "ICVEncoderConfig", "LMM_PRESETS",
-    "load_icv_for_inference",
+    "load_icv_for_inference", "collate_token_ids", "check_batch_contract",
 ]
 __version__ = "0.1.0"

@@ -183,3 +183,38 @@ def test_checkpoint_wire_format_round_trip(tmp_path):
     assert seen == [4.0, 4.0, 2.0, 2.0, 1.5, 1.5, 1.5] and float(dec.temperature) == 1.5
     with pytest.raises(NotImplementedError):
         VQAICVModule(Iface(), ModuleConfig(learnable_t=True), lmm)
+
+
+def test_collator_contract_from_token_ids():
+    """f4: the four-key batch of icv_datamodule.py:125-130 from pre-tokenised samples, and the
+    invariant that both get_mask calls select the same rows."""
+    from licv_vqa_b200.collate import check_batch_contract, collate_token_ids
+    from oracle import licv_oracle as O
+    BOS, EOS, PAD = 1, 2, 0
+    query_x = [[BOS, 11, 12, 13], [BOS, 21, 22]]                      # question, no answer
+    query = [[BOS, 11, 12, 13, 90, 91], [BOS, 21, 22, 95]]            # question + answer
+    ice = [[BOS, 50, 51, 52, 53, 54], [BOS, 60, 61]]                  # in-context examples
+    batch = collate_token_ids(query, query_x, ice, PAD, BOS, EOS)
+    q, t = batch["query_inputs"]["input_ids"], batch["inputs"]["input_ids"]
+    assert q.tolist() == [[1, 11, 12, 13, 90, 91, 2], [1, 21, 22, 95, 2, 0, 0]]
+    assert t[0].tolist() == [1, 50, 51, 52, 53, 54, 11, 12, 13, 90, 91, 2]
+    assert t[1].tolist() == [1, 60, 61, 21, 22, 95, 2, 0, 0, 0, 0, 0]
+    assert batch["query_inputs"]["attention_mask"].tolist() == [[1] * 7, [1, 1, 1, 1, 1, 0, 0]]
+    assert batch["query_x_length"].tolist() == [4, 3]                 # non-pad tokens of query_x
+    assert batch["in_context_length"].tolist() == [6 + 3, 3 + 2]      # ICE + query_x without its BOS
+    assert check_batch_contract(batch, PAD) == 3 + 2                  # answer tokens + EOS per sample
+    # the same selection the oracle's get_mask / pair_rows make
+    sm = O.get_mask(q.numpy(), batch["query_x_length"].numpy(), PAD)
+    tm = O.get_mask(t.numpy(), batch["in_context_length"].numpy(), PAD)
+    ktr = O.pair_rows(sm, tm)
+    assert (ktr >= 0).sum() == 5
+    flat_t = t.reshape(-1).numpy()
+    assert flat_t[ktr[ktr >= 0]].tolist() == q.reshape(-1).numpy()[ktr >= 0].tolist()   # same tokens
+    # a broken batch is refused
+    bad = dict(batch, in_context_length=batch["in_context_length"] + 1)
+    with pytest.raises(ValueError, match="rows"):
+        check_batch_contract(bad, PAD)
+    with pytest.raises(ValueError, match="missing"):
+        check_batch_contract({"inputs": batch["inputs"]}, PAD)
+    left = collate_token_ids(query, query_x, ice, PAD, BOS, EOS, padding_side="left")
+    assert left["query_inputs"]["input_ids"][1].tolist() == [0, 0, 1, 21, 22, 95, 2]

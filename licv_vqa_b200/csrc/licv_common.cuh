@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "licv_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -178,6 +180,44 @@ struct GridCapScope {
     explicit GridCapScope(int cap) : saved(tl_grid_cap) { tl_grid_cap = cap; }
     ~GridCapScope() { tl_grid_cap = saved; }
 };
+
+// ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL)
+// ---------------------------------------------------------------------------------------------
+// The hot kernels are launched with the programmatic-stream-serialization attribute: their CTAs
+// may be scheduled, and run their prologue (barrier init, index arithmetic), while the previous
+// kernel in the stream is still draining; `pdl_wait()` is the point after which the previous
+// kernel's memory operations are complete and visible - it must precede the first access to
+// global memory.  `pdl_launch_dependents()` lets the NEXT kernel begin its own prologue.  At the
+// training shape (2-6 MB per launch) the gaps between launches are a third of the step.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char* v = std::getenv("LICV_PDL");
+        return !(v && v[0] == '0');
+    }();
+    return on;
+}
+// fills `attr` (room for 2) for a launch with an optional cluster dimension; returns the count
+inline int launch_attrs(cudaLaunchAttribute* attr, int cluster) {
+    int n = 0;
+    if (cluster > 0) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    return n;
+}
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

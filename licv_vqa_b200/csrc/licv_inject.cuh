@@ -169,6 +169,8 @@ __global__ void __launch_bounds__(kCtaThreads, 2) fwd_kernel(Args a) {
     float* my_slab0 = slab[0] + (grp * (gt >> 5)) * P;
     float* my_slab1 = slab[1] + (grp * (gt >> 5)) * P;
 
+    pdl_launch_dependents();
+    pdl_wait();   // the previous kernel's results (h, the shift, ...) are visible from here on
     float s[VPT][EPV];
     load_shift<HDT, VPT, RND>(a.shift, nvec, tg, gt, s);
 
@@ -260,6 +262,8 @@ __global__ void __launch_bounds__(kCtaThreads, 2) bwd_kernel(Args a) {
     float* my_slab0 = slab[0] + (grp * (gt >> 5)) * P;
     float* my_slab1 = slab[1] + (grp * (gt >> 5)) * P;
 
+    pdl_launch_dependents();
+    pdl_wait();   // the previous kernel's results (h, the shift, ...) are visible from here on
     float s[VPT][EPV];
     load_shift<HDT, VPT, RND>(a.shift, nvec, tg, gt, s);
 

@@ -26,8 +26,14 @@ int launch_fwd(const Args& a0, const Launch& L) {
     const int64_t need = ((L.n_tok + TB - 1) / TB + groups - 1) / groups;
     Args a = a0;
     a.gt = L.plan.gt;
-    kern<<<(int)(need < cap ? need : cap), threads, 0, L.stream>>>(a);
-    return (int)cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(need < cap ? need : cap));
+    cfg.blockDim = dim3(threads);
+    cfg.stream = L.stream;
+    cudaLaunchAttribute attr[2];
+    cfg.attrs = attr;
+    cfg.numAttrs = launch_attrs(attr, 0);
+    return (int)cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 template <int HDT, int GDT, int VPT, int TB, int RND>
@@ -52,8 +58,15 @@ int launch_bwd(const Args& a0, const Launch& L) {
     const int64_t need = ((L.n_tok + tok_per_group - 1) / tok_per_group + groups - 1) / groups;
     Args a = a0;
     a.gt = L.plan.gt;
-    kern<<<(int)(need < cap ? need : cap), threads, smem, L.stream>>>(a);
-    return (int)cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(need < cap ? need : cap));
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = L.stream;
+    cudaLaunchAttribute attr[2];
+    cfg.attrs = attr;
+    cfg.numAttrs = launch_attrs(attr, 0);
+    return (int)cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 // tokens staged per iteration: one while there are too few tokens to fill the machine, else
@@ -116,13 +129,9 @@ int launch_bwd_pipe(const Args& a, const Launch& L) {
     cfg.blockDim = dim3(kPipeThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = L.stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = C;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
-    cfg.numAttrs = C > 1 ? 1 : 0;
+    cfg.numAttrs = launch_attrs(attr, C > 1 ? C : 0);
     // resident CTAs: whole clusters that fit the device at once
     static int64_t cap = 0;
     static size_t cap_smem = 0;

@@ -140,7 +140,9 @@ __global__ void __launch_bounds__(kPipeThreads, 3) bwd_pipe_kernel(PipeArgs pa) 
         for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
         mbar_init_fence();
     }
+    pdl_launch_dependents();
     __syncthreads();
+    pdl_wait();   // everything above ran while the previous kernel drained; global memory from here
 
     uint64_t policy = 0;
     // issue the copies of this CTA's `it`-th batch into stage it % S

@@ -374,7 +374,9 @@ __global__ void __launch_bounds__(NT, (NV <= 4 ? 768 / NT : 1)) kd_loss_cluster_
         mbar_init(&xbar[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_launch_dependents();
     cluster_sync_all();   // every peer's barriers exist before the first message
+    pdl_wait();           // the previous kernel's logits / row lists are visible from here on
     // Reduction 1 has two (slots, mbarrier) sets used alternately by row parity: on CE-only rows
     // nothing separates one row's reduction 1 from the next row's, so a fast peer may send its
     // next partial while this CTA has not yet received (or a slow warp here still reads) all the
@@ -720,13 +722,9 @@ int launch_cluster(const KdArgs& a, int C, cudaStream_t st) {
     cfg.blockDim = dim3(NT);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = C;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;   // st.async / mapa are cluster instructions: C = 1 is launched as a cluster too
+    cudaLaunchAttribute attr[2];
+    cfg.attrs = attr;   // st.async / mapa are cluster instructions: C = 1 is launched as a cluster too
+    cfg.numAttrs = launch_attrs(attr, C);
     // clusters resident at once (per instantiation and cluster size; one process drives one GPU)
     static int64_t cap[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (cap[C] == 0) {

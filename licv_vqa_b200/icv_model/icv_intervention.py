@@ -97,16 +97,21 @@ class LearnableICVInterventionLMM(nn.Module):
         for name in self.intervention_layer_names:
             if name not in named:
                 raise LookupError(name)  # what baukit raises for an unknown layer name
+        # any earlier wrapper with hooks anywhere in this tower is retired first (it may sit behind
+        # another interface object and on other submodules, e.g. layers vs their MLPs)
+        for mod in named.values():
+            previous = mod.__dict__.get("_licv_hook_owner")
+            previous = previous() if previous is not None else None
+            if previous is not None and previous is not self:
+                previous.remove_hooks()
+                mod.__dict__.pop("_licv_hook_owner", None)
+        for name in self.intervention_layer_names:
             # the reference keys the ICV row by the FIRST number in the module name
             # (icv_intervention.py:63), KeyError included when that is not a hooked layer id
             layer_idx = int(re.findall(r"\d+", name)[0])
             icv_index = self.layer_to_icv_index[layer_idx]
             # ownership is recorded on the hooked submodule itself (the same tower may sit behind
             # different interface objects)
-            previous = named[name].__dict__.get("_licv_hook_owner")
-            previous = previous() if previous is not None else None
-            if previous is not None and previous is not self:
-                previous.remove_hooks()
             named[name].__dict__["_licv_hook_owner"] = weakref.ref(self)
             self._hook_handles.append(
                 named[name].register_forward_hook(self._make_hook(icv_index)))
@@ -171,8 +176,16 @@ class LearnableICVInterventionLMM(nn.Module):
                 raise TypeError("'NoneType' object is not subscriptable: intervention is enabled "
                                 "but no icv was given")
             self._active = _ActiveICV(icv)
-            # stays armed after the call for checkpoint recomputation during backward
-            return fn(*args, **kwargs)
+            armed_for_backward = torch.is_grad_enabled() and icv.requires_grad
+            try:
+                return fn(*args, **kwargs)
+            finally:
+                # a training forward stays armed: activation-checkpoint recomputation during
+                # backward must re-inject (the reference's context manager has removed its hooks
+                # by then, icv_intervention.py:112-113).  Anything else (generate, no-grad
+                # evaluation) disarms like the reference's `with` block does.
+                if not armed_for_backward:
+                    self._active = previous
         self._active = None
         try:
             return fn(*args, **kwargs)

@@ -219,6 +219,22 @@ inline int launch_attrs(cudaLaunchAttribute* attr, int cluster) {
     return n;
 }
 
+// <<<grid, block, smem, stream>>> with the PDL attribute; the kernel must call pdl_wait() before
+// its first global-memory access
+template <typename... KArgs, typename... Args>
+inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                      Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    cfg.attrs = attr;
+    cfg.numAttrs = launch_attrs(attr, 0);
+    return (int)cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace licv

@@ -85,6 +85,8 @@ __device__ __forceinline__ void fence_acq_rel_sys() {
 
 __global__ void __launch_bounds__(kDpThreads) dp_exchange_kernel(DpArgs a) {
     __shared__ float slab[kDpThreads / 32];
+    licv::pdl_launch_dependents();
+    licv::pdl_wait();
     // control block of this rank: {step, ticket0, ticket1, error}
     unsigned long long* step_ctr = reinterpret_cast<unsigned long long*>(a.local + a.ctl_off);
     unsigned* ticket0 = reinterpret_cast<unsigned*>(a.local + a.ctl_off + 8);
@@ -272,8 +274,7 @@ extern "C" int licv_dp_allreduce_adamw(licv_dp_comm* c, float* param, float* gra
     a.world = c->world;
     a.prescale = 1.0f / (float)c->world;
     a.partial = reinterpret_cast<float*>(c->region[c->rank] + L.partial_off);
-    dp_exchange_kernel<<<kDpCtas, kDpThreads, 0, st>>>(a);
-    if (cudaError_t e = cudaGetLastError()) return (int)e;
+    if (int rc = licv::launch_pdl(dp_exchange_kernel, dim3(kDpCtas), dim3(kDpThreads), 0, st, a)) return rc;
     return licv::launch_adamw_after_norm(param, grad, exp_avg, exp_avg_sq, n_vec, n_alpha, lr_vec,
                                          lr_alpha, beta1, beta2, eps, weight_decay, step,
                                          1.0f / (float)c->world, max_grad_norm, norm_out, workspace,

@@ -44,6 +44,8 @@ __device__ __forceinline__ float sigmoidf(float a) { return 1.0f / (1.0f + __exp
 
 __global__ void icv_scale_kernel(const float* __restrict__ alpha, const float* __restrict__ vec,
                                  float* __restrict__ icv, int n_layers, int d, int use_sigmoid) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t n4 = (int64_t)n_layers * d / 4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -61,6 +63,8 @@ __global__ void __launch_bounds__(256)
 icv_scale_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ vec,
                      const float* __restrict__ d_icv, float* __restrict__ d_vec,
                      float* __restrict__ d_alpha, int d, int use_sigmoid) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float slab[8];
     const int l = blockIdx.x;
     float a = alpha[l];
@@ -93,6 +97,8 @@ icv_scale_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ 
 
 __global__ void get_mask_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ len,
                                 int64_t pad, int batch, int seq, uint8_t* __restrict__ mask) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int n = batch * seq;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int b = i / seq, t = i - b * seq;
@@ -124,6 +130,8 @@ kd_prepare_rows_kernel(const int64_t* __restrict__ s_ids, const int64_t* __restr
                        int ce_variant, int batch, int Tq, int Tt, int32_t* __restrict__ kl_tea_row,
                        int64_t* __restrict__ ce_label, int32_t* __restrict__ counts,
                        int32_t* __restrict__ tea_sel) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ int32_t stu_by_rank[];  // [batch*Tq]: flat student row of the k-th KL row
     __shared__ int warp_tot[32];
     __shared__ int s_m;
@@ -203,6 +211,8 @@ kd_prepare_rows_kernel(const int64_t* __restrict__ s_ids, const int64_t* __restr
 // ---- optimizer ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float* __restrict__ g, int64_t n, float prescale, float* __restrict__ acc) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float slab[8];
     float s = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -233,6 +243,8 @@ struct AdamArgs {
 };
 
 __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     // every CTA reads the norm before taking a ticket; the last ticket holder clears the workspace
     float coef = a.prescale;
     float sumsq;
@@ -317,9 +329,8 @@ extern "C" int licv_icv_scale(const float* alpha_raw, const float* vec, float* i
     if (!aligned16(vec) || !aligned16(icv)) return LICV_ERR_MISALIGNED;
     const int64_t n4 = (int64_t)n_layers * d / 4;
     const int grid = (int)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184);
-    icv_scale_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        alpha_raw, vec, icv, n_layers, d, use_sigmoid);
-    return (int)cudaGetLastError();
+    return launch_pdl(icv_scale_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                      alpha_raw, vec, icv, n_layers, d, use_sigmoid);
 }
 
 extern "C" int licv_icv_scale_bwd(const float* alpha_raw, const float* vec, const float* d_icv,
@@ -330,9 +341,9 @@ extern "C" int licv_icv_scale_bwd(const float* alpha_raw, const float* vec, cons
     if (n_layers == 0) return LICV_OK;
     if (!alpha_raw || !vec || !d_icv || !d_vec) return LICV_ERR_NULL_POINTER;
     if (!aligned16(vec) || !aligned16(d_icv) || !aligned16(d_vec)) return LICV_ERR_MISALIGNED;
-    icv_scale_bwd_kernel<<<n_layers, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        alpha_raw, vec, d_icv, d_vec, d_alpha_raw, d, use_sigmoid);
-    return (int)cudaGetLastError();
+    return launch_pdl(icv_scale_bwd_kernel, dim3(n_layers), dim3(256), 0,
+                      reinterpret_cast<cudaStream_t>(stream), alpha_raw, vec, d_icv, d_vec, d_alpha_raw,
+                      d, use_sigmoid);
 }
 
 extern "C" int licv_get_mask(const int64_t* input_ids, const int64_t* mask_length,
@@ -344,9 +355,8 @@ extern "C" int licv_get_mask(const int64_t* input_ids, const int64_t* mask_lengt
     if (!input_ids || !mask_length || !mask) return LICV_ERR_NULL_POINTER;
     const int n = batch * seq_len;
     const int grid = (n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184;
-    get_mask_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        input_ids, mask_length, pad_token_id, batch, seq_len, mask);
-    return (int)cudaGetLastError();
+    return launch_pdl(get_mask_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                      input_ids, mask_length, pad_token_id, batch, seq_len, mask);
 }
 
 extern "C" int licv_kd_select_rows(const int64_t* stu_ids, const int64_t* stu_mask_length,
@@ -387,10 +397,8 @@ extern "C" int licv_kd_select_rows(const int64_t* stu_ids, const int64_t* stu_ma
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         });
     }
-    kd_prepare_rows_kernel<<<1, 1024, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        stu_ids, stu_mask_length, stu_attention_mask, tea_ids, tea_mask_length, pad_token_id,
-        image_token_id, ce_variant, batch, stu_len, tea_len, kl_tea_row, ce_label, counts, tea_sel);
-    return (int)cudaGetLastError();
+    return launch_pdl(kd_prepare_rows_kernel, dim3(1), dim3(1024), smem,
+                      reinterpret_cast<cudaStream_t>(stream), stu_ids, stu_mask_length, stu_attention_mask, tea_ids, tea_mask_length, pad_token_id, image_token_id, ce_variant, batch, stu_len, tea_len, kl_tea_row, ce_label, counts, tea_sel);
 }
 
 namespace licv {
@@ -415,8 +423,7 @@ int launch_adamw_after_norm(float* param, const float* grad, float* exp_avg, flo
     a.acc = static_cast<float*>(workspace);
     a.ticket = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + 4);
     const int grid = (int)((n + 1023) / 1024 < 148 ? (n + 1023) / 1024 : 148);
-    adamw_kernel<<<grid, 256, 0, st>>>(a);
-    return (int)cudaGetLastError();
+    return launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, st, a);
 }
 }  // namespace licv
 
@@ -432,7 +439,9 @@ extern "C" int licv_adamw_step(float* param, const float* grad, float* exp_avg, 
     if (!param || !grad || !exp_avg || !exp_avg_sq || !workspace) return LICV_ERR_NULL_POINTER;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = (int)((n + 1023) / 1024 < 148 ? (n + 1023) / 1024 : 148);
-    sumsq_kernel<<<grid, 256, 0, st>>>(grad, n, grad_prescale, static_cast<float*>(workspace));
+    if (int rc = launch_pdl(sumsq_kernel, dim3(grid), dim3(256), 0, st, grad, n, grad_prescale,
+                            static_cast<float*>(workspace)))
+        return rc;
     return launch_adamw_after_norm(param, grad, exp_avg, exp_avg_sq, n_vec, n_alpha, lr_vec, lr_alpha,
                                    beta1, beta2, eps, weight_decay, step, grad_prescale,
                                    max_grad_norm, norm_out, workspace, nullptr, 0, st);

@@ -166,7 +166,7 @@ int dispatch_bwd_pipe_tb(const Args& a, const Launch& L) {
     constexpr int TBbig = kFit >= 4 ? 4 : (kFit >= 2 ? 2 : 1);
     static const int forced_tb = env_int("LICV_PIPE_TB", 0);   // tuning knob: 1 = one token per stage
     const int64_t fill = (int64_t)device_info().sm_count * 2;
-    if (TBbig > 1 && forced_tb != 1 && L.n_tok >= fill * TBbig)
+    if (TBbig > 1 && forced_tb != 1 && (forced_tb > 1 || L.n_tok >= fill * TBbig))
         return launch_bwd_pipe<HDT, GDT, VPT, TBbig, RND>(a, L);
     return launch_bwd_pipe<HDT, GDT, VPT, 1, RND>(a, L);
 }

@@ -35,6 +35,7 @@
 //
 // Not a dense contraction: no tensor cores; bounds are HBM, then the SFU and FMA pipes.
 #include <cstdlib>
+#include <type_traits>
 
 #include "licv_common.cuh"
 #include "licv_kd_loss.cuh"
@@ -701,6 +702,381 @@ __global__ void __launch_bounds__(NT, (NV <= 4 ? 768 / NT : 1)) kd_loss_cluster_
     }
 }
 
+// =================================================================================================
+// Variant: ONE CTA per SM owns a whole row pair; no cross-SM synchronisation at all.
+//
+// A row pair of 32k 16-bit logits needs 256 KB of fp32 cache (e_s and e_t / kl_w w), more than
+// the 227 KB of shared memory - but an SM also has 256 KB of TENSOR MEMORY (512 columns x 128
+// lanes x 32 bit), readable and writable from registers with tcgen05.ld / tcgen05.st (SASS LDTM /
+// STTM).  Here e_s lives in shared memory (128 KB, thread-private float4 slots) and e_t / w in
+// TMEM (256 columns = 128 KB: thread t of warp w owns 64 columns of lane 32 (w % 4) + t), so the
+// three sweeps of a row run inside one 512-thread CTA and the two row-wide reductions are plain
+// CTA barriers among 16 warps of the same SM - the cluster kernel above loses ~45 % of its time
+// waiting for the slowest of 32 warps spread over 8 SMs.  The raw logits of the next row are
+// prefetched into registers right after sweep B.  16-bit logits, V <= 32760.
+// =================================================================================================
+constexpr int kMT = 512;            // threads per CTA
+constexpr int kMW = kMT / 32;       // 16 warps: 4 per TMEM lane quarter
+constexpr int kMNV = 8;             // 16-byte vectors per thread and row (64 elements)
+constexpr int kMCols = 256;         // TMEM columns allocated (64 per warp column group)
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                   "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_st() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kMT, 1) kd_loss_tmem_kernel(KdArgs a) {
+    constexpr int EPV = Fmt<DT>::kPerVec;   // 8
+    constexpr int EB = Fmt<DT>::kBytes;     // 2
+    constexpr int NV = kMNV;
+    constexpr int kStep = kMT * EPV;
+    static_assert(EPV == 8, "16-bit logits only");
+    extern __shared__ __align__(16) float4 cs[];           // [NV * 2][kMT]: e_s, fp32
+    __shared__ __align__(16) float4 part[2][kMW];
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_tot[2 * kMW];
+    __shared__ int s_last;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&s_tmem)),
+                     "n"(kMCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    pdl_launch_dependents();
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // this thread's 64 columns: lane quarter of the warp, column group of the warp
+    const uint32_t tcol = s_tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+    pdl_wait();
+
+    const float T = a.temperature;
+    const float inv_t = 1.0f / T;
+    const bool round_tempered = (a.round_flags & LICV_ROUND_TEMPERED) && T != 1.0f;
+    const int64_t n_kl = a.counts ? (int64_t)a.counts[0] : a.n_kl;
+    const int64_t n_ce = a.counts ? (int64_t)a.counts[1] : a.n_ce;
+    const bool use_kl = !a.only_hard_loss;
+    const bool use_ce = a.ce_label != nullptr;
+    const float kl_w = use_kl ? a.grad_scale * T / (float)n_kl : 0.f;
+    const float ce_w = use_ce ? a.grad_scale * (a.only_hard_loss ? 1.0f : a.hard_loss_weight) /
+                                    (float)n_ce
+                              : 0.f;
+    const float eps = a.kl_eps;
+    float* row_kl = a.row_loss;
+    float* row_ce = a.row_loss + a.n_rows;
+    const int V = a.vocab;
+
+    auto fetch_tr = [&](int64_t r) -> int {
+        if (!use_kl || r >= a.n_rows) return -1;
+        return a.kl_tea_row ? a.kl_tea_row[r] : (int)r;
+    };
+    auto fetch_lab = [&](int64_t r) -> int {
+        if (!use_ce || r >= a.n_rows) return kLabNone;
+        const int64_t l = a.ce_label[r];
+        return (l < -100 || l > 0x7fffffff) ? kLabBad : (int)l;
+    };
+    auto x_row = [&](int64_t r) { return static_cast<const char*>(a.stu) + (size_t)r * a.stu_stride * EB; };
+    auto t_row = [&](int tr) { return static_cast<const char*>(a.tea) + (size_t)tr * a.tea_stride * EB; };
+    auto g_row = [&](int64_t r) { return static_cast<char*>(a.dstu) + (size_t)r * a.stu_stride * EB; };
+    auto phase16 = [](const void* p) { return (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u); };
+    auto j_first = [&](const char* xr) -> int { return tid * EPV - (int)(phase16(xr) / EB); };
+    auto all_full = [&](int j0) -> bool { return j0 >= 0 && j0 + (NV - 1) * kStep + EPV <= V; };
+
+    uint4 xs[NV], xt[NV];
+    auto load_raw = [&](int64_t r, int tr, int lab) {
+        if (tr < 0 && lab == kLabNone) return;
+        const char* xr = x_row(r);
+        const int j0 = j_first(xr);
+        const bool full = all_full(j0);
+        if (full) {
+            const char* px = xr + (int64_t)j0 * EB;
+#pragma unroll
+            for (int k = 0; k < NV; ++k)
+                xs[k] = ld_stream(reinterpret_cast<const uint4*>(px + (size_t)k * kStep * EB));
+        } else {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) xs[k] = load_row_vec<DT>(xr, j0 + k * kStep, V, 16);
+        }
+        if (tr >= 0) {
+            const char* tp = t_row(tr);
+            const uint32_t dph = (phase16(tp) - phase16(xr)) & 15u;
+            if (full && dph == 0) {
+                const char* pt = tp + (int64_t)j0 * EB;
+#pragma unroll
+                for (int k = 0; k < NV; ++k)
+                    xt[k] = ld_stream(reinterpret_cast<const uint4*>(pt + (size_t)k * kStep * EB));
+            } else {
+                const int align = dph == 0 ? 16 : (int)(dph & (0u - dph));
+#pragma unroll
+                for (int k = 0; k < NV; ++k) xt[k] = load_row_vec<DT>(tp, j0 + k * kStep, V, align);
+            }
+        }
+    };
+    auto thread_max = [&](const uint4 (&raw)[NV], float it_row, bool rnd) -> int {
+        RawMax<DT> mx;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) mx.add(raw[k]);
+        float m = mx.get() * it_row;
+        if (rnd) m = Fmt<DT>::round(m);
+        m = fminf(fmaxf(ceilf(m * kLog2e), -1.0e6f), 1.0e6f);
+        return (int)m;
+    };
+    // CTA-wide reductions: warp partials through shared memory, one barrier each
+    auto cta_mz = [&](MZ2 v, float4* slab) -> MZ2 {
+        const MZ2 w = mz_warp(v);
+        if (lane == 0) slab[warp] = make_float4(__int_as_float(w.ms), w.zs, __int_as_float(w.mt), w.zt);
+        __syncthreads();
+        const float4 p = slab[lane & (kMW - 1)];
+        MZ2 c{__float_as_int(p.x), p.y, __float_as_int(p.z), p.w};
+#pragma unroll
+        for (int o = kMW / 2; o > 0; o >>= 1) {
+            MZ2 b;
+            b.ms = __shfl_xor_sync(0xffffffffu, c.ms, o);
+            b.zs = __shfl_xor_sync(0xffffffffu, c.zs, o);
+            b.mt = __shfl_xor_sync(0xffffffffu, c.mt, o);
+            b.zt = __shfl_xor_sync(0xffffffffu, c.zt, o);
+            c = mz_join(c, b);
+        }
+        return c;
+    };
+    auto cta_sum2 = [&](float x, float y, float4* slab) -> float2 {
+        x = warp_sum(x);
+        y = warp_sum(y);
+        if (lane == 0) slab[warp] = make_float4(x, y, 0.f, 0.f);
+        __syncthreads();
+        const float4 p = slab[lane & (kMW - 1)];
+        float sx = p.x, sy = p.y;
+#pragma unroll
+        for (int o = kMW / 2; o > 0; o >>= 1) {
+            sx += __shfl_xor_sync(0xffffffffu, sx, o);
+            sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        }
+        return make_float2(sx, sy);
+    };
+
+    int64_t r = blockIdx.x;
+    const int64_t stride = gridDim.x;
+    int tr = fetch_tr(r), lab = fetch_lab(r);
+    if (r < a.n_rows) load_raw(r, tr, lab);
+    int tr_n = fetch_tr(r + stride), lab_n = fetch_lab(r + stride);
+    for (; r < a.n_rows; r += stride) {
+        const int64_t rn = r + stride;
+        const bool has_kl = tr >= 0, has_ce = lab != kLabNone;
+        const char* xr = x_row(r);
+        const int j0 = j_first(xr);
+        const bool full = all_full(j0);
+        char* gp = a.dstu ? g_row(r) : nullptr;
+        const bool g_vec = gp && phase16(gp) == phase16(xr);
+        auto store_grad = [&](int k, const float* gr) {
+            if (full && g_vec)
+                st_vec(reinterpret_cast<uint4*>(gp + ((int64_t)j0 + (int64_t)k * kStep) * EB), pack<DT>(gr));
+            else
+                store_row_vec<DT>(gp, j0 + k * kStep, V, g_vec, gr);
+        };
+        if (!has_kl && !has_ce) {
+            if (gp) {
+                float z[EPV];
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) z[e] = 0.f;
+#pragma unroll
+                for (int k = 0; k < NV; ++k) store_grad(k, z);
+            }
+            if (tid == 0) { row_kl[r] = 0.f; row_ce[r] = 0.f; }
+        } else {
+            const float it_row = has_kl ? inv_t : 1.0f;
+            const bool rnd_row = has_kl && round_tempered;
+            const float c_row = rnd_row ? kLog2e : kLog2e * it_row;
+            const bool lab_ok = has_ce && lab >= 0 && lab < V;
+            float x_lab = 0.f;
+            if (tid == 0 && lab_ok) x_lab = load_elem<DT>(xr, lab);
+
+            // ---- sweep B: e_s -> shared memory, e_t -> tensor memory --------------------------
+            MZ2 mine{kNoMaxI, 0.f, kNoMaxI, 0.f};
+            mine.ms = thread_max(xs, it_row, rnd_row);
+            {
+                const float m = (float)mine.ms;
+                auto body = [&](auto rnd_tag) {
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) {
+                        float x[EPV];
+                        unpack<DT>(xs[k], x);
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e) {
+                            float u = x[e];
+                            if (decltype(rnd_tag)::value) u = Fmt<DT>::round(u * it_row);
+                            x[e] = ex2(fmaf(u, c_row, -m));
+                            mine.zs += x[e];
+                        }
+                        cs[(k * 2) * kMT + tid] = make_float4(x[0], x[1], x[2], x[3]);
+                        cs[(k * 2 + 1) * kMT + tid] = make_float4(x[4], x[5], x[6], x[7]);
+                    }
+                };
+                if (rnd_row) body(std::true_type{}); else body(std::false_type{});
+            }
+            if (has_kl) {
+                mine.mt = thread_max(xt, it_row, rnd_row);
+                const float m = (float)mine.mt;
+                auto body = [&](auto rnd_tag) {
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) {
+                        float x[EPV];
+                        unpack<DT>(xt[k], x);
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e) {
+                            float u = x[e];
+                            if (decltype(rnd_tag)::value) u = Fmt<DT>::round(u * it_row);
+                            x[e] = ex2(fmaf(u, c_row, -m));
+                            mine.zt += x[e];
+                        }
+                        tmem_st8(tcol + k * 8, x);
+                    }
+                };
+                if (rnd_row) body(std::true_type{}); else body(std::false_type{});
+                tmem_wait_st();
+            }
+            // the raw registers are free: request the next row
+            if (rn < a.n_rows) load_raw(rn, tr_n, lab_n);
+            const int tr_nn = fetch_tr(rn + stride), lab_nn = fetch_lab(rn + stride);
+
+            // ---- reduction 1 (one CTA barrier) ------------------------------------------------
+            const MZ2 tot = cta_mz(mine, part[0]);
+            const float fs = pow2i(mine.ms - tot.ms) * rcp(tot.zs);
+
+            // ---- sweep C ----------------------------------------------------------------------
+            float W = 0.f, kl_row = 0.f;
+            if (has_kl) {
+                const float ft = pow2i(mine.mt - tot.mt) * rcp(tot.zt);
+                float klp = 0.f, wp = 0.f;
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                    const float4 e0 = cs[(k * 2) * kMT + tid], e1 = cs[(k * 2 + 1) * kMT + tid];
+                    const float ea[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                    float eb[8];
+                    tmem_ld8(tcol + k * 8, eb);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float q = ea[e] * fs;
+                        const float p = eb[e] * ft;
+                        const float rq = rcp(q + eps);
+                        klp = fmaf(p, lg2((p + eps) * rq), klp);
+                        const float w = p * q * rq;
+                        wp += w;
+                        eb[e] = w * kl_w;
+                    }
+                    if (gp) tmem_st8(tcol + k * 8, eb);
+                }
+                tmem_wait_st();
+                const float2 r2 = cta_sum2(klp, wp, part[1]);
+                kl_row = r2.x * kLn2;
+                W = r2.y;
+            }
+
+            // ---- sweep D ----------------------------------------------------------------------
+            if (gp) {
+                const float ce_on = has_ce ? ce_w : 0.f;
+                const float A = fs * fmaf(kl_w, W, ce_on);
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                    const float4 e0 = cs[(k * 2) * kMT + tid], e1 = cs[(k * 2 + 1) * kMT + tid];
+                    const float ea[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                    float wk[8];
+                    if (has_kl) {
+                        tmem_ld8(tcol + k * 8, wk);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) wk[e] = 0.f;
+                    }
+                    float gr[EPV];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) gr[e] = fmaf(ea[e], A, -wk[e]);
+                    if (has_ce) {
+                        const unsigned rel = (unsigned)(lab - (j0 + k * kStep));
+                        if (rel < (unsigned)EPV && lab >= 0) {
+#pragma unroll
+                            for (int e = 0; e < EPV; ++e)
+                                if (e == (int)rel) gr[e] -= ce_on;
+                        }
+                    }
+                    store_grad(k, gr);
+                }
+            }
+            if (tid == 0) {
+                row_kl[r] = kl_row;
+                float ce = 0.f;
+                if (has_ce)
+                    ce = lab_ok ? ((float)tot.ms + lg2(tot.zs)) * kLn2 - x_lab : __int_as_float(0x7fc00000);
+                row_ce[r] = ce;
+            }
+            tr = tr_n; lab = lab_n;
+            tr_n = tr_nn; lab_n = lab_nn;
+            // no barrier here: the caches are thread-private and each of part[0] / part[1] is
+            // rewritten only after the OTHER reduction's barrier, which every reader has passed
+            continue;
+        }
+        tr = tr_n; lab = lab_n;
+        if (rn < a.n_rows) load_raw(rn, tr, lab);
+        tr_n = fetch_tr(rn + stride); lab_n = fetch_lab(rn + stride);
+    }
+
+    // TMEM is released by the warp that allocated it, after every warp is done with it
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(kMCols)
+                     : "memory");
+    }
+    // ---- the last CTA to finish reduces the per-row losses (fixed order: deterministic) --------
+    if (tid == 0) {
+        __threadfence();
+        const unsigned done_ctas = atomicAdd(a.counter, 1u);
+        s_last = (done_ctas == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        float tk = 0.f, tc = 0.f;
+        for (int64_t i = tid; i < a.n_rows; i += kMT) {
+            tk += __ldcg(row_kl + i);
+            tc += __ldcg(row_ce + i);
+        }
+        tk = warp_sum(tk);
+        tc = warp_sum(tc);
+        if (lane == 0) { s_tot[warp] = tk; s_tot[kMW + warp] = tc; }
+        __syncthreads();
+        if (tid == 0) {
+            tk = 0.f; tc = 0.f;
+            for (int w = 0; w < kMW; ++w) { tk += s_tot[w]; tc += s_tot[kMW + w]; }
+            const float kl = use_kl ? tk * T * T / (float)n_kl : 0.f;
+            const float ce = use_ce ? tc / (float)n_ce : 0.f;
+            a.out_losses[0] = kl;
+            a.out_losses[1] = ce;
+            a.out_losses[2] = a.only_hard_loss ? ce : (use_ce ? fmaf(a.hard_loss_weight, ce, kl) : kl);
+            *a.counter = 0u;
+        }
+    }
+}
+
 inline int env_int(const char* name, int dflt) {
     const char* v = std::getenv(name);
     return v ? std::atoi(v) : dflt;
@@ -764,6 +1140,43 @@ int dispatch_nv(const KdArgs& a, int C, int NV, int NT, cudaStream_t st) {
     }
 }
 
+template <int DT>
+int launch_tmem(const KdArgs& a, cudaStream_t st) {
+    auto kern = kd_loss_tmem_kernel<DT>;
+    constexpr size_t smem = (size_t)kMNV * 2 * kMT * sizeof(float4);   // 128 KB
+    static bool raised = false;
+    if (!raised) {
+        const cudaError_t e =
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        raised = true;
+    }
+    int64_t grid = a.n_rows < device_info().sm_count ? a.n_rows : device_info().sm_count;
+    if (grid < 1) grid = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kMT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    cfg.attrs = attr;
+    cfg.numAttrs = launch_attrs(attr, 0);
+    return (int)cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+}  // namespace
+
+bool kd_tmem_plan(int vocab, int dtype, float temperature, bool kl_and_ce) {
+    static const int on = env_int("LICV_KD_TMEM", 0);
+    if (!on || dtype == LICV_F32) return false;
+    if (kl_and_ce && temperature != 1.0f) return false;
+    return (int64_t)(vocab + 7) / 8 + 1 <= (int64_t)kMNV * kMT;    // 4096 vectors of 8
+}
+int launch_kd_tmem(const KdArgs& a, int dtype, cudaStream_t st) {
+    return dtype == LICV_BF16 ? launch_tmem<LICV_BF16>(a, st) : launch_tmem<LICV_F16>(a, st);
+}
+
+namespace {
 }  // namespace
 
 #ifdef LICV_TRACE

@@ -29,7 +29,8 @@ int launch_kd_generic(const KdArgs& a, int dtype, cudaStream_t st);
 // cluster kernel (licv_kd_loss_cluster.cu): does a row of `vocab` elements fit a cluster, and how
 bool kd_cluster_plan(int vocab, int dtype, float temperature, bool kl_and_ce, int* C, int* NV,
                      int* NT);
-// experimental: one CTA per SM, the row cached in shared memory + tensor memory (LICV_KD_TMEM=1)
+// one CTA per SM, the row cached in shared memory + tensor memory: 16-bit logits, V <= 32760
+// (LICV_KD_TMEM=0 disables it)
 bool kd_tmem_plan(int vocab, int dtype, float temperature, bool kl_and_ce);
 int launch_kd_tmem(const KdArgs& a, int dtype, cudaStream_t st);
 int launch_kd_cluster(const KdArgs& a, int dtype, int C, int NV, int NT, cudaStream_t st);

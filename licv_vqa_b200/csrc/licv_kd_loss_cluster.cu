@@ -124,60 +124,126 @@ template <> __device__ __forceinline__ uint32_t neg_inf_word<LICV_F32>() { retur
 template <> __device__ __forceinline__ uint32_t neg_inf_word<LICV_BF16>() { return 0xff80ff80u; }
 template <> __device__ __forceinline__ uint32_t neg_inf_word<LICV_F16>() { return 0xfc00fc00u; }
 
-// raw element bits <-> position inside a 16-byte vector
-template <int DT>
-__device__ __forceinline__ void put_elem(uint4& v, int e, uint32_t bits) {
-    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
-    if (Fmt<DT>::kBytes == 4) {
-        w[e] = bits;
-    } else {
-        const int sh = (e & 1) * 16;
-        w[e >> 1] = (w[e >> 1] & ~(0xffffu << sh)) | (bits << sh);
-    }
-}
 template <int DT>
 __device__ __forceinline__ uint32_t load_bits(const char* row, int64_t j) {
     if (Fmt<DT>::kBytes == 4) return reinterpret_cast<const uint32_t*>(row)[j];
     return reinterpret_cast<const uint16_t*>(row)[j];
 }
 
-// One 16-byte vector's worth of elements j0 .. j0+EPV-1 of a row (elements outside [0, V) read
-// as -inf).  `align`: guaranteed alignment in bytes of (row + j0 * EB) for interior vectors.
+// 16 bytes at p, which is aligned to `align` bytes (16, 8, 4 or 2)
+__device__ __forceinline__ uint4 load_vec_any(const char* p, int align) {
+    if (align >= 16) return ld_stream(reinterpret_cast<const uint4*>(p));
+    if (align >= 8) {
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
+        const uint2 b = __ldg(reinterpret_cast<const uint2*>(p) + 1);
+        return make_uint4(a.x, a.y, b.x, b.y);
+    }
+    if (align >= 4) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+        return make_uint4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+    }
+    const uint16_t* q = reinterpret_cast<const uint16_t*>(p);
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = (uint32_t)__ldg(q + 2 * i) | ((uint32_t)__ldg(q + 2 * i + 1) << 16);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// elements of the vector that starts at row element j0 and lie outside [0, V) become -inf
 template <int DT>
-__device__ __forceinline__ uint4 load_row_vec(const char* row, int j0, int V, int align) {
+__device__ __forceinline__ uint4 mask_vec(uint4 v, int j0, int V) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+    const uint32_t ninf = neg_inf_word<DT>();
+    if constexpr (Fmt<DT>::kBytes == 4) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if ((unsigned)(j0 + e) >= (unsigned)V) w[e] = ninf;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool lo = (unsigned)(j0 + 2 * i) < (unsigned)V, hi = (unsigned)(j0 + 2 * i + 1) < (unsigned)V;
+            w[i] = ((lo ? w[i] : ninf) & 0xffffu) | ((hi ? w[i] : ninf) & 0xffff0000u);
+        }
+    }
+    return v;
+}
+
+// This thread's NV vectors of one row: elements j0 + k * kStep .. + EPV - 1, k < NV.
+// (row + j0 * EB) is aligned to `align` bytes.  load_row_vecs only ISSUES the loads;
+// mask_row_vecs, called where the registers are first consumed, turns the elements outside [0, V)
+// into -inf.
+//
+// Two rules, both measured (8192 x 32002 bf16 rows: 630 us without them, 540 us with):
+//  * control flow is decided per WARP (from lane 0's element index), never per thread: a warp
+//    whose lanes take different load paths into the same destination registers stalls at the
+//    second path until the first path's loads have landed (write-after-write);
+//  * nothing here may read a loaded register: the loads are the next row's prefetch, issued in
+//    the middle of the current row, and the warp at a row end would wait a full HBM round trip
+//    for them - every other warp of the row then waits for it at the next barrier.
+//
+// A warp that straddles a row end therefore loads whole vectors from clamped addresses.  With
+// align == 16 such a vector is the 16-byte granule that holds the row's first or last element,
+// so the bytes of it that lie outside the row are read (and discarded by the mask) too: they
+// belong to the neighbouring row or, for the first / last row of a buffer, to the same 16-byte
+// granule of the allocation - never to another page.  With align < 16 (a teacher row whose
+// 16-byte phase differs from the student row's) the boundary vector is read element by element
+// from clamped indices, nothing outside the row is touched, and that one path does consume its
+// loads early.
+template <int DT>
+__device__ __forceinline__ bool warp_inside_row(int j0, int kStep, int nv, int V, int lane) {
+    const int jw = j0 - lane * Fmt<DT>::kPerVec;           // lane 0's first element
+    return jw >= 0 && jw + (nv - 1) * kStep + 32 * Fmt<DT>::kPerVec <= V;
+}
+
+template <int DT, int NV>
+__device__ __forceinline__ void load_row_vecs(uint4 (&out)[NV], const char* row, int j0, int kStep, int V,
+                                              int align, int lane) {
     constexpr int EPV = Fmt<DT>::kPerVec;
     constexpr int EB = Fmt<DT>::kBytes;
     const uint32_t ninf = neg_inf_word<DT>();
-    uint4 v = make_uint4(ninf, ninf, ninf, ninf);
-    if (j0 >= V || j0 + EPV <= 0) return v;
-    const char* p = row + (int64_t)j0 * EB;
-    if (j0 >= 0 && j0 + EPV <= V) {
-        if (align >= 16) {
-            v = ld_stream(reinterpret_cast<const uint4*>(p));
-        } else if (align >= 8) {
-            const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
-            const uint2 b = __ldg(reinterpret_cast<const uint2*>(p) + 1);
-            v = make_uint4(a.x, a.y, b.x, b.y);
-        } else if (align >= 4) {
-            const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
-            v = make_uint4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+    const char* p0 = row + (int64_t)j0 * EB;
+    if (warp_inside_row<DT>(j0, kStep, NV, V, lane)) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) out[k] = load_vec_any(p0 + (size_t)k * kStep * EB, align);
+        return;
+    }
+    const int jw = j0 - lane * EPV;
+    // first and last vector that overlap the row (same 16-byte phase as j0)
+    const int jmin = -((-j0) & (EPV - 1));
+    const int jmax = jmin + ((V - 1 - jmin) & ~(EPV - 1));
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int jk = j0 + k * kStep, jwk = jw + k * kStep;
+        if (jwk >= 0 && jwk + 32 * EPV <= V) {
+            out[k] = load_vec_any(p0 + (size_t)k * kStep * EB, align);
+        } else if (jwk >= V || jwk + 32 * EPV <= 0) {
+            out[k] = make_uint4(ninf, ninf, ninf, ninf);
+        } else if (align >= 16) {
+            const int jc = min(max(jk, jmin), jmax);
+            out[k] = ld_stream(reinterpret_cast<const uint4*>(row + (int64_t)jc * EB));
         } else {
-            const uint16_t* q = reinterpret_cast<const uint16_t*>(p);
-            uint32_t w[4];
+            uint32_t bits[EPV];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                w[i] = (uint32_t)__ldg(q + 2 * i) | ((uint32_t)__ldg(q + 2 * i + 1) << 16);
-            v = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int e = 0; e < EPV; ++e) bits[e] = load_bits<DT>(row, min(max(jk + e, 0), V - 1));
+            if constexpr (EB == 4) {
+                out[k] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+            } else {
+                out[k] = make_uint4(bits[0] | (bits[1] << 16), bits[2] | (bits[3] << 16),
+                                    bits[4] | (bits[5] << 16), bits[6] | (bits[7] << 16));
+            }
         }
-        return v;
     }
-    // first / last vector of the row: element by element
+}
+
+template <int DT, int NV>
+__device__ __forceinline__ void mask_row_vecs(uint4 (&v)[NV], int j0, int kStep, int V, int lane) {
+    if (warp_inside_row<DT>(j0, kStep, NV, V, lane)) return;
+    const int jw = j0 - lane * Fmt<DT>::kPerVec;
 #pragma unroll
-    for (int e = 0; e < EPV; ++e) {
-        const int j = j0 + e;
-        if (j >= 0 && j < V) put_elem<DT>(v, e, load_bits<DT>(row, j));
+    for (int k = 0; k < NV; ++k) {
+        const int jwk = jw + k * kStep;
+        if (jwk < 0 || jwk + 32 * Fmt<DT>::kPerVec > V) v[k] = mask_vec<DT>(v[k], j0 + k * kStep, V);
     }
-    return v;
 }
 
 template <int DT>
@@ -432,29 +498,11 @@ __global__ void __launch_bounds__(NT, (NV <= 4 ? 768 / NT : 1)) kd_loss_cluster_
         if (tr < 0 && lab == kLabNone) return;
         const char* xr = x_row(r);
         const int j0 = j_first(xr);
-        const bool full = all_full(j0);
-        if (full) {
-            const char* px = xr + (int64_t)j0 * EB;
-#pragma unroll
-            for (int k = 0; k < NV; ++k)
-                xs[k] = ld_stream(reinterpret_cast<const uint4*>(px + (size_t)k * kStep * EB));
-        } else {
-#pragma unroll
-            for (int k = 0; k < NV; ++k) xs[k] = load_row_vec<DT>(xr, j0 + k * kStep, V, 16);
-        }
+        load_row_vecs<DT, NV>(xs, xr, j0, kStep, V, 16, tid & 31);
         if (tr >= 0) {
             const char* tp = t_row(tr);
             const uint32_t dph = (phase16(tp) - phase16(xr)) & 15u;
-            if (full && dph == 0) {
-                const char* pt = tp + (int64_t)j0 * EB;
-#pragma unroll
-                for (int k = 0; k < NV; ++k)
-                    xt[k] = ld_stream(reinterpret_cast<const uint4*>(pt + (size_t)k * kStep * EB));
-            } else {
-                const int align = dph == 0 ? 16 : (int)(dph & (0u - dph));   // 8, 4 or 2
-#pragma unroll
-                for (int k = 0; k < NV; ++k) xt[k] = load_row_vec<DT>(tp, j0 + k * kStep, V, align);
-            }
+            load_row_vecs<DT, NV>(xt, tp, j0, kStep, V, dph == 0 ? 16 : (int)(dph & (0u - dph)), tid & 31);
         }
     };
     auto store_grad = [&](char* gr_row, bool g_vec, int j0, bool full, int k, const float* gr) {
@@ -554,6 +602,8 @@ __global__ void __launch_bounds__(NT, (NV <= 4 ? 768 / NT : 1)) kd_loss_cluster_
 
             // ---- sweep B: exponentials relative to the thread's own maxima -> cache -----------
             MZ2 mine{kNoMaxI, 0.f, kNoMaxI, 0.f};
+            mask_row_vecs<DT, NV>(xs, j_first(x_row(r)), kStep, V, tid & 31);
+            if (has_kl) mask_row_vecs<DT, NV>(xt, j_first(x_row(r)), kStep, V, tid & 31);
             mine.ms = thread_max(xs, it_row, rnd_row);
             mine.zs = sweep_b(xs, (float)mine.ms, c_row, it_row, rnd_row, cs);
             if (has_kl) {
@@ -715,11 +765,48 @@ __global__ void __launch_bounds__(NT, (NV <= 4 ? 768 / NT : 1)) kd_loss_cluster_
 // waiting for the slowest of 32 warps spread over 8 SMs.  The raw logits of the next row are
 // prefetched into registers right after sweep B.  16-bit logits, V <= 32760.
 // =================================================================================================
-constexpr int kMT = 512;            // threads per CTA
-constexpr int kMW = kMT / 32;       // 16 warps: 4 per TMEM lane quarter
-constexpr int kMNV = 8;             // 16-byte vectors per thread and row (64 elements)
-constexpr int kMCols = 256;         // TMEM columns allocated (64 per warp column group)
+// (threads, 16-byte vectors per thread and row): 512 x 8, 768 x 6 or 1024 x 4; warp w owns TMEM lane
+// quarter w % 4 and the column group w / 4 (8 NV columns wide)
+__host__ __device__ constexpr int tmem_cols(int threads, int nv) {
+    return (threads / 128) * nv * 8 <= 256 ? 256 : 512;     // allocations are powers of two
+}
 
+// 16 consecutive columns of this thread's TMEM lane <-> 16 registers.  tcgen05.ld is asynchronous:
+// the registers are valid only after tcgen05.wait::ld, so the wait is written as an asm that
+// "modifies" them - the compiler cannot move a use above it.
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+        "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+        "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+        "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+          "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+                   "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]),
+                   "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
                  "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
@@ -727,26 +814,28 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
                  "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-    uint32_t r[8];
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
                    "=r"(r[7])
                  : "r"(taddr)
                  : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void tmem_wait_st() {
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+                   "+r"(r[7])
+                 :
+                 : "memory");
 }
 
-template <int DT>
+template <int DT, int kMT, int kMNV>
 __global__ void __launch_bounds__(kMT, 1) kd_loss_tmem_kernel(KdArgs a) {
     constexpr int EPV = Fmt<DT>::kPerVec;   // 8
     constexpr int EB = Fmt<DT>::kBytes;     // 2
     constexpr int NV = kMNV;
+    constexpr int kMW = kMT / 32;
+    constexpr int kMCols = tmem_cols(kMT, kMNV);
     constexpr int kStep = kMT * EPV;
     static_assert(EPV == 8, "16-bit logits only");
     extern __shared__ __align__(16) float4 cs[];           // [NV * 2][kMT]: e_s, fp32
@@ -768,7 +857,7 @@ __global__ void __launch_bounds__(kMT, 1) kd_loss_tmem_kernel(KdArgs a) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // this thread's 64 columns: lane quarter of the warp, column group of the warp
-    const uint32_t tcol = s_tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+    const uint32_t tcol = s_tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * (NV * 8));
     pdl_wait();
 
     const float T = a.temperature;
@@ -808,29 +897,11 @@ __global__ void __launch_bounds__(kMT, 1) kd_loss_tmem_kernel(KdArgs a) {
         if (tr < 0 && lab == kLabNone) return;
         const char* xr = x_row(r);
         const int j0 = j_first(xr);
-        const bool full = all_full(j0);
-        if (full) {
-            const char* px = xr + (int64_t)j0 * EB;
-#pragma unroll
-            for (int k = 0; k < NV; ++k)
-                xs[k] = ld_stream(reinterpret_cast<const uint4*>(px + (size_t)k * kStep * EB));
-        } else {
-#pragma unroll
-            for (int k = 0; k < NV; ++k) xs[k] = load_row_vec<DT>(xr, j0 + k * kStep, V, 16);
-        }
+        load_row_vecs<DT, NV>(xs, xr, j0, kStep, V, 16, lane);
         if (tr >= 0) {
             const char* tp = t_row(tr);
             const uint32_t dph = (phase16(tp) - phase16(xr)) & 15u;
-            if (full && dph == 0) {
-                const char* pt = tp + (int64_t)j0 * EB;
-#pragma unroll
-                for (int k = 0; k < NV; ++k)
-                    xt[k] = ld_stream(reinterpret_cast<const uint4*>(pt + (size_t)k * kStep * EB));
-            } else {
-                const int align = dph == 0 ? 16 : (int)(dph & (0u - dph));
-#pragma unroll
-                for (int k = 0; k < NV; ++k) xt[k] = load_row_vec<DT>(tp, j0 + k * kStep, V, align);
-            }
+            load_row_vecs<DT, NV>(xt, tp, j0, kStep, V, dph == 0 ? 16 : (int)(dph & (0u - dph)), lane);
         }
     };
     auto thread_max = [&](const uint4 (&raw)[NV], float it_row, bool rnd) -> int {
@@ -847,32 +918,25 @@ __global__ void __launch_bounds__(kMT, 1) kd_loss_tmem_kernel(KdArgs a) {
         const MZ2 w = mz_warp(v);
         if (lane == 0) slab[warp] = make_float4(__int_as_float(w.ms), w.zs, __int_as_float(w.mt), w.zt);
         __syncthreads();
-        const float4 p = slab[lane & (kMW - 1)];
-        MZ2 c{__float_as_int(p.x), p.y, __float_as_int(p.z), p.w};
-#pragma unroll
-        for (int o = kMW / 2; o > 0; o >>= 1) {
-            MZ2 b;
-            b.ms = __shfl_xor_sync(0xffffffffu, c.ms, o);
-            b.zs = __shfl_xor_sync(0xffffffffu, c.zs, o);
-            b.mt = __shfl_xor_sync(0xffffffffu, c.mt, o);
-            b.zt = __shfl_xor_sync(0xffffffffu, c.zt, o);
-            c = mz_join(c, b);
+        MZ2 c{kNoMaxI, 0.f, kNoMaxI, 0.f};
+        if (lane < kMW) {
+            const float4 p = slab[lane];
+            c = MZ2{__float_as_int(p.x), p.y, __float_as_int(p.z), p.w};
         }
-        return c;
+        return mz_warp(c);
     };
     auto cta_sum2 = [&](float x, float y, float4* slab) -> float2 {
         x = warp_sum(x);
         y = warp_sum(y);
         if (lane == 0) slab[warp] = make_float4(x, y, 0.f, 0.f);
         __syncthreads();
-        const float4 p = slab[lane & (kMW - 1)];
-        float sx = p.x, sy = p.y;
-#pragma unroll
-        for (int o = kMW / 2; o > 0; o >>= 1) {
-            sx += __shfl_xor_sync(0xffffffffu, sx, o);
-            sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        float sx = 0.f, sy = 0.f;
+        if (lane < kMW) {
+            const float4 p = slab[lane];
+            sx = p.x;
+            sy = p.y;
         }
-        return make_float2(sx, sy);
+        return make_float2(warp_sum(sx), warp_sum(sy));
     };
 
     int64_t r = blockIdx.x;
@@ -913,6 +977,8 @@ __global__ void __launch_bounds__(kMT, 1) kd_loss_tmem_kernel(KdArgs a) {
 
             // ---- sweep B: e_s -> shared memory, e_t -> tensor memory --------------------------
             MZ2 mine{kNoMaxI, 0.f, kNoMaxI, 0.f};
+            mask_row_vecs<DT, NV>(xs, j0, kStep, V, lane);
+            if (has_kl) mask_row_vecs<DT, NV>(xt, j0, kStep, V, lane);
             mine.ms = thread_max(xs, it_row, rnd_row);
             {
                 const float m = (float)mine.ms;
@@ -955,36 +1021,44 @@ __global__ void __launch_bounds__(kMT, 1) kd_loss_tmem_kernel(KdArgs a) {
                 if (rnd_row) body(std::true_type{}); else body(std::false_type{});
                 tmem_wait_st();
             }
-            // the raw registers are free: request the next row
-            if (rn < a.n_rows) load_raw(rn, tr_n, lab_n);
-            const int tr_nn = fetch_tr(rn + stride), lab_nn = fetch_lab(rn + stride);
-
             // ---- reduction 1 (one CTA barrier) ------------------------------------------------
             const MZ2 tot = cta_mz(mine, part[0]);
             const float fs = pow2i(mine.ms - tot.ms) * rcp(tot.zs);
+            // the raw registers are free: request the next row (after the reduction, so that
+            // nothing the reduction needs has to live across this burst of loads)
+            if (rn < a.n_rows) load_raw(rn, tr_n, lab_n);
+            const int tr_nn = fetch_tr(rn + stride), lab_nn = fetch_lab(rn + stride);
 
             // ---- sweep C ----------------------------------------------------------------------
             float W = 0.f, kl_row = 0.f;
             if (has_kl) {
                 const float ft = pow2i(mine.mt - tot.mt) * rcp(tot.zt);
                 float klp = 0.f, wp = 0.f;
+                // e_t comes back from tensor memory two vectors at a time, one load ahead of the
+                // arithmetic
+                uint32_t tb[2][8];
+                tmem_ld8_issue(tcol, tb[0]);
 #pragma unroll
                 for (int k = 0; k < NV; ++k) {
-                    const float4 e0 = cs[(k * 2) * kMT + tid], e1 = cs[(k * 2 + 1) * kMT + tid];
-                    const float ea[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-                    float eb[8];
-                    tmem_ld8(tcol + k * 8, eb);
+                    tmem_ld_wait(tb[k & 1]);
+                    if (k + 1 < NV) tmem_ld8_issue(tcol + (k + 1) * 8, tb[(k + 1) & 1]);
+                    float wk[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float q = ea[e] * fs;
-                        const float p = eb[e] * ft;
-                        const float rq = rcp(q + eps);
-                        klp = fmaf(p, lg2((p + eps) * rq), klp);
-                        const float w = p * q * rq;
-                        wp += w;
-                        eb[e] = w * kl_w;
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 es = cs[(k * 2 + h) * kMT + tid];
+                        const float ea[4] = {es.x, es.y, es.z, es.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float q = ea[e] * fs;
+                            const float p = __uint_as_float(tb[k & 1][4 * h + e]) * ft;
+                            const float rq = rcp(q + eps);
+                            klp = fmaf(p, lg2((p + eps) * rq), klp);
+                            const float w = p * q * rq;
+                            wp += w;
+                            wk[4 * h + e] = w * kl_w;
+                        }
                     }
-                    if (gp) tmem_st8(tcol + k * 8, eb);
+                    if (gp) tmem_st8(tcol + k * 8, wk);
                 }
                 tmem_wait_st();
                 const float2 r2 = cta_sum2(klp, wp, part[1]);
@@ -996,20 +1070,22 @@ __global__ void __launch_bounds__(kMT, 1) kd_loss_tmem_kernel(KdArgs a) {
             if (gp) {
                 const float ce_on = has_ce ? ce_w : 0.f;
                 const float A = fs * fmaf(kl_w, W, ce_on);
+                uint32_t tb[2][8];
+                if (has_kl) tmem_ld8_issue(tcol, tb[0]);
 #pragma unroll
                 for (int k = 0; k < NV; ++k) {
+                    if (has_kl) {
+                        tmem_ld_wait(tb[k & 1]);
+                        if (k + 1 < NV) tmem_ld8_issue(tcol + (k + 1) * 8, tb[(k + 1) & 1]);
+                    }
                     const float4 e0 = cs[(k * 2) * kMT + tid], e1 = cs[(k * 2 + 1) * kMT + tid];
                     const float ea[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-                    float wk[8];
-                    if (has_kl) {
-                        tmem_ld8(tcol + k * 8, wk);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) wk[e] = 0.f;
-                    }
                     float gr[EPV];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) gr[e] = fmaf(ea[e], A, -wk[e]);
+                    for (int e = 0; e < 8; ++e) {
+                        const float wk = has_kl ? __uint_as_float(tb[k & 1][e]) : 0.f;
+                        gr[e] = fmaf(ea[e], A, -wk);
+                    }
                     if (has_ce) {
                         const unsigned rel = (unsigned)(lab - (j0 + k * kStep));
                         if (rel < (unsigned)EPV && lab >= 0) {
@@ -1140,10 +1216,10 @@ int dispatch_nv(const KdArgs& a, int C, int NV, int NT, cudaStream_t st) {
     }
 }
 
-template <int DT>
+template <int DT, int MT, int MNV>
 int launch_tmem(const KdArgs& a, cudaStream_t st) {
-    auto kern = kd_loss_tmem_kernel<DT>;
-    constexpr size_t smem = (size_t)kMNV * 2 * kMT * sizeof(float4);   // 128 KB
+    auto kern = kd_loss_tmem_kernel<DT, MT, MNV>;
+    constexpr size_t smem = (size_t)MNV * 2 * MT * sizeof(float4);   // e_s: 128-144 KB
     static bool raised = false;
     if (!raised) {
         const cudaError_t e =
@@ -1155,7 +1231,7 @@ int launch_tmem(const KdArgs& a, cudaStream_t st) {
     if (grid < 1) grid = 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kMT);
+    cfg.blockDim = dim3(MT);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -1163,17 +1239,24 @@ int launch_tmem(const KdArgs& a, cudaStream_t st) {
     cfg.numAttrs = launch_attrs(attr, 0);
     return (int)cudaLaunchKernelEx(&cfg, kern, a);
 }
+template <int DT>
+int launch_tmem_shape(const KdArgs& a, cudaStream_t st) {
+    static const int threads = env_int("LICV_KD_TMEM_THREADS", 512);
+    if (threads == 1024) return launch_tmem<DT, 1024, 4>(a, st);
+    if (threads == 768) return launch_tmem<DT, 768, 6>(a, st);
+    return launch_tmem<DT, 512, 8>(a, st);
+}
 
 }  // namespace
 
 bool kd_tmem_plan(int vocab, int dtype, float temperature, bool kl_and_ce) {
-    static const int on = env_int("LICV_KD_TMEM", 0);
+    static const int on = env_int("LICV_KD_TMEM", 1);   // 0: always the cluster kernel
     if (!on || dtype == LICV_F32) return false;
     if (kl_and_ce && temperature != 1.0f) return false;
-    return (int64_t)(vocab + 7) / 8 + 1 <= (int64_t)kMNV * kMT;    // 4096 vectors of 8
+    return (int64_t)(vocab + 7) / 8 + 1 <= 4096;    // vectors of 8 elements a CTA holds
 }
 int launch_kd_tmem(const KdArgs& a, int dtype, cudaStream_t st) {
-    return dtype == LICV_BF16 ? launch_tmem<LICV_BF16>(a, st) : launch_tmem<LICV_F16>(a, st);
+    return dtype == LICV_BF16 ? launch_tmem_shape<LICV_BF16>(a, st) : launch_tmem_shape<LICV_F16>(a, st);
 }
 
 namespace {

@@ -14,7 +14,7 @@ def main():
     lib = _abi.load()
     st = torch.cuda.current_stream().cuda_stream
     dt, code = torch.bfloat16, _abi.BF16
-    d, V = 4096, 32002
+    d, V = 4096, int(os.environ.get("LICV_PROFILE_VOCAB", "32002"))
     s = torch.randn(d, device="cuda")
     ds = torch.zeros(d, device="cuda")
     toks = [int(x) for x in os.environ.get("LICV_PROFILE_TOKENS", "32768,256").split(",")]

@@ -837,12 +837,14 @@ __global__ void __launch_bounds__(kMT, 1) kd_loss_tmem_kernel(KdArgs a) {
     constexpr int kMW = kMT / 32;
     constexpr int kMCols = tmem_cols(kMT, kMNV);
     constexpr int kStep = kMT * EPV;
+    constexpr int kMeta = 64;
     static_assert(EPV == 8, "16-bit logits only");
     extern __shared__ __align__(16) float4 cs[];           // [NV * 2][kMT]: e_s, fp32
     __shared__ __align__(16) float4 part[2][kMW];
     __shared__ uint32_t s_tmem;
     __shared__ float s_tot[2 * kMW];
     __shared__ int s_last;
+    __shared__ int s_tr[kMeta], s_lab[kMeta];               // (teacher row, label) of the next rows
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (warp == 0) {
@@ -941,11 +943,29 @@ __global__ void __launch_bounds__(kMT, 1) kd_loss_tmem_kernel(KdArgs a) {
 
     int64_t r = blockIdx.x;
     const int64_t stride = gridDim.x;
-    int tr = fetch_tr(r), lab = fetch_lab(r);
+    // Row descriptors come from shared memory, refilled kMeta rows at a time: a label load issued
+    // behind the next row's prefetch and narrowed at once stalled every warp for a full HBM round
+    // trip per row (6 % of the kernel in one IADD3), and carrying the raw 64-bit label a row
+    // instead costs two registers this kernel does not have.
+    auto fill_meta = [&](int64_t r0) {
+        __syncthreads();
+        if (tid < kMeta) {
+            const int64_t rr = r0 + (int64_t)tid * stride;
+            s_tr[tid] = fetch_tr(rr);
+            s_lab[tid] = fetch_lab(rr);
+        }
+        __syncthreads();
+    };
+    int it = 0, meta0 = 0;                                  // this CTA's row ordinal, first cached ordinal
+    fill_meta(r);
+    int tr = s_tr[0], lab = s_lab[0];
     if (r < a.n_rows) load_raw(r, tr, lab);
-    int tr_n = fetch_tr(r + stride), lab_n = fetch_lab(r + stride);
-    for (; r < a.n_rows; r += stride) {
+    for (; r < a.n_rows; r += stride, ++it) {
         const int64_t rn = r + stride;
+        if (it + 1 - meta0 == kMeta) {
+            fill_meta(rn);
+            meta0 = it + 1;
+        }
         const bool has_kl = tr >= 0, has_ce = lab != kLabNone;
         const char* xr = x_row(r);
         const int j0 = j_first(xr);
@@ -1026,8 +1046,8 @@ __global__ void __launch_bounds__(kMT, 1) kd_loss_tmem_kernel(KdArgs a) {
             const float fs = pow2i(mine.ms - tot.ms) * rcp(tot.zs);
             // the raw registers are free: request the next row (after the reduction, so that
             // nothing the reduction needs has to live across this burst of loads)
+            const int tr_n = s_tr[it + 1 - meta0], lab_n = s_lab[it + 1 - meta0];
             if (rn < a.n_rows) load_raw(rn, tr_n, lab_n);
-            const int tr_nn = fetch_tr(rn + stride), lab_nn = fetch_lab(rn + stride);
 
             // ---- sweep C ----------------------------------------------------------------------
             float W = 0.f, kl_row = 0.f;
@@ -1105,14 +1125,12 @@ __global__ void __launch_bounds__(kMT, 1) kd_loss_tmem_kernel(KdArgs a) {
                 row_ce[r] = ce;
             }
             tr = tr_n; lab = lab_n;
-            tr_n = tr_nn; lab_n = lab_nn;
             // no barrier here: the caches are thread-private and each of part[0] / part[1] is
             // rewritten only after the OTHER reduction's barrier, which every reader has passed
             continue;
         }
-        tr = tr_n; lab = lab_n;
+        tr = s_tr[it + 1 - meta0]; lab = s_lab[it + 1 - meta0];
         if (rn < a.n_rows) load_raw(rn, tr, lab);
-        tr_n = fetch_tr(rn + stride); lab_n = fetch_lab(rn + stride);
     }
 
     // TMEM is released by the warp that allocated it, after every warp is done with it

@@ -395,7 +395,8 @@ def bandwidth_shapes(hp, peak):
         t = sum(ts) / len(ts)
         out.append({"kernel": name, "shape": f"n_tok={n_tok} d={d} {CFG['dtype']}",
                     "achieved": nbytes / t / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": nbytes / t / 1e9 / peak, "us": t * 1e6})
+                    "frac": nbytes / t / 1e9 / peak, "frac_of_nominal_8tbs": nbytes / t / 8e12,
+                    "us": t * 1e6})
     del h, g, o
     R = 4096
     stu = [(torch.randn(R, V, device=hp.device) * 3).to(dt) for _ in range(2)]
@@ -417,7 +418,8 @@ def bandwidth_shapes(hp, peak):
     nbytes = 3 * es * R * V
     out.append({"kernel": "licv_kd_loss_fwd_bwd", "shape": f"R={R} KL+CE rows V={V} {CFG['dtype']}",
                 "achieved": nbytes / t / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": nbytes / t / 1e9 / peak, "us": t * 1e6})
+                "frac": nbytes / t / 1e9 / peak, "frac_of_nominal_8tbs": nbytes / t / 8e12,
+                "us": t * 1e6})
     return out
 
 
@@ -652,6 +654,7 @@ def main():
         roofline = {"bound": "hbm", "kernel": "licv_inject_bwd",
                     "achieved": bytes_bwd / t_bwd / 1e9, "peak": peak, "unit": "GB/s",
                     "frac": bytes_bwd / t_bwd / 1e9 / peak,
+                    "frac_of_nominal_8tbs": bytes_bwd / t_bwd / 8e12,
                     "traffic": load_traffic("licv_inject_bwd@256tok"),
                     "traffic_note": "ncu --set full capture of the same launch shape (bf16): DRAM "
                                     "reads = the algorithmic h + g; the dh write-back is still in "

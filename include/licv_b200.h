@@ -179,7 +179,7 @@ int licv_scale_inplace(void* x, int64_t n, const float* scale, int dtype, licv_s
 /* ------------------------------------------------------------------------------------------
  * f2 ("next" row)  optimizer step on the flat ICV parameter buffer
  *   replaces torch.optim.AdamW / DeepSpeedCPUAdam + gradient_clip_val + the cosine warm-up
- *   schedule (icv_src/icv_module.py:171-209, config/trainer/*.yaml) for the L*d + L trainable
+ *   schedule (icv_src/icv_module.py:171-209, config/trainer/{ddp,zero2}.yaml) for the L*d + L trainable
  *   floats.  flat layout: [vec (n_vec floats) | alpha (n_alpha floats)].
  *   grad is first multiplied by grad_prescale (1/world_size after the all-reduce sum), then
  *   clipped to global L2 norm max_grad_norm (<= 0 disables), then AdamW with lr_vec / lr_alpha.

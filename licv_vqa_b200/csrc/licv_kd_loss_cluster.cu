@@ -47,7 +47,6 @@ constexpr int kMaxT = 256;            // threads per CTA: 256, or 128 (more, sma
 constexpr int kMaxWarps = kMaxT / 32;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
-constexpr float kNoMax = -3.0e38f;   // "no element yet": finite, so differences never give NaN
 
 __device__ __forceinline__ float ex2(float x) {
     float y;
@@ -489,9 +488,10 @@ __global__ void __launch_bounds__(NT, (NV <= 4 ? 768 / NT : 1)) kd_loss_cluster_
     auto j_first = [&](const char* xr) -> int {
         return (((int)rank * NV) * kT + tid) * EPV - (int)(phase16(xr) / EB);
     };
-    // every one of this thread's vectors lies wholly inside the row (all but the threads at the
-    // row's two ends): no per-vector range checks
-    auto all_full = [&](int j0) -> bool { return j0 >= 0 && j0 + (NV - 1) * kStep + EPV <= V; };
+    // every vector of every lane of this warp lies wholly inside the row: no per-vector checks.
+    // Decided per warp, like the loads: a lane that took the slow store path on its own made its
+    // warp run both paths for all NV vectors and arrive late at the row's next barrier.
+    auto all_full = [&](int j0) -> bool { return warp_inside_row<DT>(j0, kStep, NV, V, tid & 31); };
 
     uint4 xs[NV], xt[NV];
     auto load_raw = [&](int64_t r, int tr, int lab) {
@@ -506,7 +506,8 @@ __global__ void __launch_bounds__(NT, (NV <= 4 ? 768 / NT : 1)) kd_loss_cluster_
         }
     };
     auto store_grad = [&](char* gr_row, bool g_vec, int j0, bool full, int k, const float* gr) {
-        if (full && g_vec)
+        const int jwk = j0 - (tid & 31) * EPV + k * kStep;          // lane 0's element of vector k
+        if (g_vec && (full || (jwk >= 0 && jwk + 32 * EPV <= V)))
             st_vec(reinterpret_cast<uint4*>(gr_row + ((int64_t)j0 + (int64_t)k * kStep) * EB), pack<DT>(gr));
         else
             store_row_vec<DT>(gr_row, j0 + k * kStep, V, g_vec, gr);
@@ -771,39 +772,9 @@ __host__ __device__ constexpr int tmem_cols(int threads, int nv) {
     return (threads / 128) * nv * 8 <= 256 ? 256 : 512;     // allocations are powers of two
 }
 
-// 16 consecutive columns of this thread's TMEM lane <-> 16 registers.  tcgen05.ld is asynchronous:
+// 8 consecutive columns of this thread's TMEM lane <-> 8 registers.  tcgen05.ld is asynchronous:
 // the registers are valid only after tcgen05.wait::ld, so the wait is written as an asm that
 // "modifies" them - the compiler cannot move a use above it.
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
-        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
-        "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
-        "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
-        "r"(__float_as_uint(v[15]))
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-          "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
-                   "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]),
-                   "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :
-                 : "memory");
-}
 __device__ __forceinline__ void tmem_wait_st() {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -892,7 +863,10 @@ __global__ void __launch_bounds__(kMT, 1) kd_loss_tmem_kernel(KdArgs a) {
     auto g_row = [&](int64_t r) { return static_cast<char*>(a.dstu) + (size_t)r * a.stu_stride * EB; };
     auto phase16 = [](const void* p) { return (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u); };
     auto j_first = [&](const char* xr) -> int { return tid * EPV - (int)(phase16(xr) / EB); };
-    auto all_full = [&](int j0) -> bool { return j0 >= 0 && j0 + (NV - 1) * kStep + EPV <= V; };
+    // every vector of every lane of this warp lies wholly inside the row: no per-vector checks.
+    // Decided per warp, like the loads: a lane that took the slow store path on its own made its
+    // warp run both paths for all NV vectors and arrive late at the row's next barrier.
+    auto all_full = [&](int j0) -> bool { return warp_inside_row<DT>(j0, kStep, NV, V, tid & 31); };
 
     uint4 xs[NV], xt[NV];
     auto load_raw = [&](int64_t r, int tr, int lab) {
@@ -973,7 +947,8 @@ __global__ void __launch_bounds__(kMT, 1) kd_loss_tmem_kernel(KdArgs a) {
         char* gp = a.dstu ? g_row(r) : nullptr;
         const bool g_vec = gp && phase16(gp) == phase16(xr);
         auto store_grad = [&](int k, const float* gr) {
-            if (full && g_vec)
+            const int jwk = j0 - lane * EPV + k * kStep;            // lane 0's element of vector k
+            if (g_vec && (full || (jwk >= 0 && jwk + 32 * EPV <= V)))
                 st_vec(reinterpret_cast<uint4*>(gp + ((int64_t)j0 + (int64_t)k * kStep) * EB), pack<DT>(gr));
             else
                 store_row_vec<DT>(gp, j0 + k * kStep, V, g_vec, gr);

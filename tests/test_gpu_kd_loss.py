@@ -142,6 +142,37 @@ def test_kd_loss_strided_rows_and_misaligned_pairs(ops):
         assert rel_err(host(dstu), want["d_stu"]) < (1e-5 if dt == "fp32" else 1.2 * EPS[dt])
 
 
+def test_kd_loss_in_place_keeps_row_padding(ops):
+    """Rows that start and end inside 16-byte granules (V = 32002 / 32003, padded strides, a view
+    that starts mid-buffer): the kernel reads whole granules at the row ends but must write only
+    the row - the sentinels around every row survive an in-place launch - and the bytes it reads
+    outside the row must not leak into the result."""
+    rng = np.random.default_rng(11)
+    for dt, V, pad, lead in [("bf16", 32002, 6, 3), ("fp16", 32003, 5, 1), ("bf16", 32002, 0, 5),
+                             ("fp32", 32002, 3, 1)]:
+        R = 9
+        stride = V + pad
+        flat = torch.full((lead + R * stride + 16,), 7.0, dtype=TD[dt], device="cuda")
+        tflat = torch.full((lead + R * stride + 16,), float("nan"), dtype=TD[dt], device="cuda")
+        stu = flat[lead:lead + R * stride].view(R, stride)[:, :V]
+        tea = tflat[lead:lead + R * stride].view(R, stride)[:, :V]
+        stu.copy_(dev(rng.normal(size=(R, V)) * 3, TD[dt]))
+        tea.copy_(dev(rng.normal(size=(R, V)) * 3, TD[dt]))
+        ktr = np.arange(R, dtype=np.int32)
+        ktr[4] = -1
+        lab = rng.integers(0, V, size=R).astype(np.int64)
+        lab[2] = -100
+        want = O.kd_loss_rows(host(stu), host(tea), ktr, lab, 1.0, 1e-6, 0.5)
+        losses, dstu = ops.kd_loss_raw(stu, tea, torch.tensor(ktr).cuda(), torch.tensor(lab).cuda(),
+                                       None, want["N"], want["M"], 1.0, 1e-6, 0.5, in_place=True)
+        assert dstu.data_ptr() == stu.data_ptr()
+        assert abs(float(losses[2]) - want["loss"]) <= 1e-5 * abs(want["loss"])
+        assert rel_err(host(dstu), want["d_stu"]) < (1e-5 if dt == "fp32" else 1.2 * EPS[dt])
+        keep = torch.ones_like(flat, dtype=torch.bool)
+        keep[lead:lead + R * stride].view(R, stride)[:, :V] = False
+        assert bool((flat[keep] == 7.0).all()), "wrote outside a row"
+
+
 def test_kd_loss_only_hard_and_empty(ops):
     rng = np.random.default_rng(6)
     R, V = 13, 1003

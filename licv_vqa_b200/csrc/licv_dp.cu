@@ -9,7 +9,7 @@
 // a cudaMalloc'd region that all peers map (CUDA IPC); ONE kernel
 //
 //   phase 0  copies the local gradient into this rank's exchange slot and, when the last CTA is
-//            done, publishes the step number into every peer's flag array (st.release.sys),
+//            done, publishes the step number into every peer's flag array (fence.sys, then relaxed stores),
 //   phase 1  waits until every peer has published the same step (ld.acquire.sys, bounded),
 //   phase 2  reads all ranks' slots over NVLink (plain 128-bit loads on mapped peer pointers),
 //            sums them in RANK ORDER (every rank gets bit-identical sums), writes the sum back
@@ -71,8 +71,8 @@ struct DpArgs {
     float* partial;       // [gridDim.x] per-CTA sums of squares (summed in fixed order later)
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
     unsigned long long v;
@@ -111,12 +111,15 @@ __global__ void __launch_bounds__(kDpThreads) dp_exchange_kernel(DpArgs a) {
         __threadfence_system();
         if (atomicAdd(ticket0, 1u) == gridDim.x - 1) {
             *ticket0 = 0u;
+            // one fence orders every CTA's slot stores (each already fenced, observed through the
+            // ticket) before the flags; the flag stores themselves are then relaxed and leave
+            // back to back - a release store per peer would pay the fence `world - 1` times
             __threadfence_system();
             for (int p = 0; p < a.world; ++p) {
                 if (p == a.rank) continue;
                 unsigned long long* flag = reinterpret_cast<unsigned long long*>(
                     const_cast<char*>(a.peer[p]) + a.flags_off) + a.rank;
-                st_release_sys(flag, step);
+                st_relaxed_sys(flag, step);
             }
         }
     }
@@ -137,11 +140,16 @@ __global__ void __launch_bounds__(kDpThreads) dp_exchange_kernel(DpArgs a) {
     // ---- phase 2: sum all ranks' slots in rank order ------------------------------------------
     float sq = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * kDpThreads + tid; i < n4; i += (int64_t)gridDim.x * kDpThreads) {
+        // every peer's value is requested before any is used: ONE NVLink round trip, not `world`
+        // of them (a loop with a run-time trip count serialises load -> add -> load)
+        float4 v[kDpMaxWorld];
+#pragma unroll
+        for (int r = 0; r < kDpMaxWorld; ++r)
+            if (r < a.world) v[r] = reinterpret_cast<const float4*>(a.peer[r] + slot_off)[i];
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < a.world; ++r) {
-            const float4 v = reinterpret_cast<const float4*>(a.peer[r] + slot_off)[i];
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
+#pragma unroll
+        for (int r = 0; r < kDpMaxWorld; ++r)
+            if (r < a.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
         reinterpret_cast<float4*>(a.grad)[i] = s;
         const float e[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll

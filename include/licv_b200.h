@@ -163,6 +163,11 @@ int licv_kd_select_rows(const int64_t* stu_ids, const int64_t* stu_mask_length,
  *   out_losses [3] fp32 device: {kl_loss, ce_loss, loss}.
  *   workspace: licv_kd_loss_workspace_bytes(R) bytes, 16-byte aligned; its first 16 bytes must be
  *        zero before the first use (the kernel leaves them zero again).
+ *   Rows may start on any element boundary (V = 32002 / 32003 do).  The kernel WRITES only the V
+ *   elements of each dstu row; it may READ the whole 16-byte-aligned granules that hold the first
+ *   and the last element of a stu / tea row (the extra bytes belong to the neighbouring row, the
+ *   row padding or, for the first / last row, the same 16-byte granule of the caller's
+ *   allocation; they never enter the result).
  * ------------------------------------------------------------------------------------------ */
 int64_t licv_kd_loss_workspace_bytes(int64_t n_rows);
 int licv_kd_loss_fwd_bwd(const void* stu, void* dstu, const void* tea, const int32_t* kl_tea_row,

@@ -5,18 +5,25 @@
 // a second collective for the logged scalars, clip_grad_norm_, AdamW (icv_src/icv_module.py:
 // 171-209, config/trainer/ddp.yaml:5,7).  The message is tiny - L*d + L (+ 4 scalars) fp32 =
 // 0.5 MB for idefics shapes - so the step is pure latency: a library all-reduce costs ~20-35 us
-// of launch + protocol against < 1 us of wire time.  Here every rank keeps its flat gradient in
-// a cudaMalloc'd region that all peers map (CUDA IPC); ONE kernel
+// of launch + protocol against < 1 us of wire time.  Here every rank owns a cudaMalloc'd region
+// that all peers map (CUDA IPC), and ONE kernel does the whole exchange with no flag, fence,
+// ticket or barrier on the way:
 //
-//   phase 0  copies the local gradient into this rank's exchange slot and, when the last CTA is
-//            done, publishes the step number into every peer's flag array (fence.sys, then relaxed stores),
-//   phase 1  waits until every peer has published the same step (ld.acquire.sys, bounded),
-//   phase 2  reads all ranks' slots over NVLink (plain 128-bit loads on mapped peer pointers),
-//            sums them in RANK ORDER (every rank gets bit-identical sums), writes the sum back
-//            as the gradient and accumulates its squared norm for the clip,
+//   push    each thread packs three gradient floats and the step number into one 16-byte packet
+//           {f0, f1, f2, tag} and stores it into the slot [step parity][this rank] of EVERY
+//           peer's region (posted writes over NVLink, one per peer, back to back);
+//   gather  the same thread reads the packets the peers pushed at the same index into its own
+//           region - local memory - until each carries this step's tag, sums the values in
+//           RANK ORDER (every rank gets bit-identical sums), writes the sum back as the
+//           gradient and accumulates its squared norm for the clip,
 //
-// and the existing AdamW kernel follows on the same stream.  Two slots alternate by step parity,
-// so a slow peer still reading step k never races a fast peer writing step k + 1; the step
+// and the existing AdamW kernel follows on the same stream.  The tag travels inside the same
+// aligned 16-byte store as the data it guards (the idea of NCCL's LL protocols), so a packet is
+// either absent or complete: the latency of the exchange is ONE one-way trip of posted writes
+// instead of copy -> system fence -> flag -> flag seen -> remote read round trip (measured, two
+// ranks, CTA 0: 1.4 + 3.5 + 6.5 + 4.3 us for those four).  Two slots per source alternate by step
+// parity: a peer can only push step k + 2 after it has finished step k + 1, which needed this
+// rank's step-k+1 packets, which are pushed after this rank finished reading step k.  The step
 // counter lives in device memory, so the launch can be replayed from a CUDA graph.
 #include <cmath>
 #include <cstring>
@@ -34,9 +41,8 @@ int launch_adamw_after_norm(float* param, const float* grad, float* exp_avg, flo
 }
 
 constexpr int kDpMaxWorld = 16;
-constexpr int kDpCtas = 128;   // all co-resident (no shared memory, 256 threads): one float4 per thread
-                               // for idefics shapes, so phase 2 is ONE NVLink round trip
 constexpr int kDpThreads = 256;
+constexpr int kDpMaxCtas = 512;   // one packet per thread for idefics shapes (171 CTAs), co-resident
 
 struct licv_dp_comm {
     int rank = 0, world = 1;
@@ -47,135 +53,168 @@ struct licv_dp_comm {
 
 namespace {
 
+// region: [parity 2][source rank kDpMaxWorld][packets * 16 B] | control block | per-CTA partials
 struct Layout {
-    int64_t slot_bytes, flags_off, ctl_off, partial_off, total;
+    int64_t n_packets, slot_bytes, ctl_off, partial_off, total;
 };
 Layout layout_of(int64_t n) {
     Layout L;
-    L.slot_bytes = ((n * 4 + 255) / 256) * 256;
-    L.flags_off = 2 * L.slot_bytes;
-    L.ctl_off = L.flags_off + kDpMaxWorld * 8;
+    L.n_packets = (n + 2) / 3;
+    L.slot_bytes = ((L.n_packets * 16 + 255) / 256) * 256;
+    L.ctl_off = 2 * kDpMaxWorld * L.slot_bytes;
     L.partial_off = L.ctl_off + 64;
-    L.total = L.partial_off + kDpCtas * 4;
+    L.total = L.partial_off + kDpMaxCtas * 4;
     return L;
+}
+int grid_of(const Layout& L) {
+    const int64_t want = (L.n_packets + kDpThreads - 1) / kDpThreads;
+    const int64_t cap = 2 * (int64_t)licv::device_info().sm_count;
+    int64_t g = want < cap ? want : cap;
+    if (g > kDpMaxCtas) g = kDpMaxCtas;
+    return (int)(g < 1 ? 1 : g);
 }
 
 struct DpArgs {
-    const char* peer[kDpMaxWorld];   // every rank's region
-    char* local;
+    char* region[kDpMaxWorld];   // every rank's region (region[rank] is local)
     float* grad;          // in: local gradient [n]; out: sum over ranks
     int64_t n, n_norm;    // floats exchanged, floats that enter the norm (the parameters)
-    int64_t slot_bytes, flags_off, ctl_off;
+    int64_t n_packets, slot_bytes, ctl_off;
     int rank, world;
     float prescale;       // 1 / world for the norm
     float* partial;       // [gridDim.x] per-CTA sums of squares (summed in fixed order later)
 };
 
-__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_packet(void* p, uint4 v) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint4 ld_packet(const void* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
     return v;
 }
-__device__ __forceinline__ void fence_acq_rel_sys() {
-    asm volatile("fence.acq_rel.sys;" ::: "memory");
+
+#ifdef LICV_TRACE
+// debug build: globaltimer at the phase boundaries of CTA 0, one record of 8 per launch (ring of 256)
+__device__ long long g_dp_trace[256 * 8];
+__device__ unsigned g_dp_trace_n;
+__device__ __forceinline__ long long dp_now() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
+#define DP_TP(k)                                                                   \
+    do {                                                                           \
+        if (blockIdx.x == 0 && threadIdx.x == 0) g_dp_trace[(trace_slot & 255) * 8 + (k)] = dp_now(); \
+    } while (0)
+#else
+#define DP_TP(k) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(kDpThreads) dp_exchange_kernel(DpArgs a) {
     __shared__ float slab[kDpThreads / 32];
+#ifdef LICV_TRACE
+    const unsigned trace_slot = g_dp_trace_n;
+    DP_TP(0);
+#endif
     licv::pdl_launch_dependents();
     licv::pdl_wait();
-    // control block of this rank: {step, ticket0, ticket1, error}
-    unsigned long long* step_ctr = reinterpret_cast<unsigned long long*>(a.local + a.ctl_off);
-    unsigned* ticket0 = reinterpret_cast<unsigned*>(a.local + a.ctl_off + 8);
-    unsigned* ticket1 = ticket0 + 1;
-    unsigned* error = ticket0 + 2;
+    DP_TP(1);
+    // control block of this rank: {step, ticket, -, error}
+    char* local = a.region[a.rank];
+    unsigned long long* step_ctr = reinterpret_cast<unsigned long long*>(local + a.ctl_off);
+    unsigned* ticket = reinterpret_cast<unsigned*>(local + a.ctl_off + 8);
+    unsigned* error = ticket + 2;
     const unsigned long long step = *step_ctr + 1;
-    const int64_t slot_off = (int64_t)(step & 1ull) * a.slot_bytes;
-    const int64_t n4 = a.n / 4;   // a.n is padded to a multiple of 4 by the host side
+    const unsigned tag = (unsigned)step;          // the regions start zeroed and steps count from 1
+    const int64_t parity_off = (int64_t)(step & 1ull) * kDpMaxWorld * a.slot_bytes;
+    const int64_t my_slot = parity_off + (int64_t)a.rank * a.slot_bytes;
     const int tid = threadIdx.x;
 
-    // ---- phase 0: my gradient -> my slot; the last CTA tells every peer -----------------------
-    {
-        const float4* src = reinterpret_cast<const float4*>(a.grad);
-        float4* dst = reinterpret_cast<float4*>(a.local + slot_off);
-        for (int64_t i = (int64_t)blockIdx.x * kDpThreads + tid; i < n4; i += (int64_t)gridDim.x * kDpThreads)
-            dst[i] = src[i];
-    }
-    // one system-scope fence per CTA (after the CTA barrier it covers every thread's stores), a
-    // ticket, and the last CTA publishes: 128 fences instead of 32768
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence_system();
-        if (atomicAdd(ticket0, 1u) == gridDim.x - 1) {
-            *ticket0 = 0u;
-            // one fence orders every CTA's slot stores (each already fenced, observed through the
-            // ticket) before the flags; the flag stores themselves are then relaxed and leave
-            // back to back - a release store per peer would pay the fence `world - 1` times
-            __threadfence_system();
-            for (int p = 0; p < a.world; ++p) {
-                if (p == a.rank) continue;
-                unsigned long long* flag = reinterpret_cast<unsigned long long*>(
-                    const_cast<char*>(a.peer[p]) + a.flags_off) + a.rank;
-                st_relaxed_sys(flag, step);
-            }
-        }
-    }
-    // ---- phase 1: every peer has published this step (bounded: a dead peer must not hang us) --
-    if (tid < a.world && tid != a.rank) {
-        const unsigned long long* flag =
-            reinterpret_cast<const unsigned long long*>(a.local + a.flags_off) + tid;
-        const long long t0 = clock64();
-        while (ld_relaxed_sys(flag) < step) {      // cheap probes, one acquire fence at the end
-            if (clock64() - t0 > (1ll << 33)) {   // ~4 s
-                *error = 1u;
-                break;
-            }
-        }
-        fence_acq_rel_sys();
-    }
-    __syncthreads();
-    // ---- phase 2: sum all ranks' slots in rank order ------------------------------------------
     float sq = 0.f;
-    for (int64_t i = (int64_t)blockIdx.x * kDpThreads + tid; i < n4; i += (int64_t)gridDim.x * kDpThreads) {
-        // every peer's value is requested before any is used: ONE NVLink round trip, not `world`
-        // of them (a loop with a run-time trip count serialises load -> add -> load)
-        float4 v[kDpMaxWorld];
+    for (int64_t i = (int64_t)blockIdx.x * kDpThreads + tid; i < a.n_packets;
+         i += (int64_t)gridDim.x * kDpThreads) {
+        float f[3];
 #pragma unroll
-        for (int r = 0; r < kDpMaxWorld; ++r)
-            if (r < a.world) v[r] = reinterpret_cast<const float4*>(a.peer[r] + slot_off)[i];
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < 3; ++k) f[k] = i * 3 + k < a.n ? a.grad[i * 3 + k] : 0.f;
+        // ---- push: one posted 16-byte write per peer ------------------------------------------
+        const uint4 pk = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), tag);
 #pragma unroll
-        for (int r = 0; r < kDpMaxWorld; ++r)
-            if (r < a.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
-        reinterpret_cast<float4*>(a.grad)[i] = s;
-        const float e[4] = {s.x, s.y, s.z, s.w};
+        for (int p = 0; p < kDpMaxWorld; ++p)
+            if (p < a.world && p != a.rank) st_packet(a.region[p] + my_slot + i * 16, pk);
+        DP_TP(2);
+        // ---- gather: the peers' packets at the same index, from LOCAL memory ------------------
+        uint4 v[kDpMaxWorld];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i * 4 + k < a.n_norm) {
-                const float x = e[k] * a.prescale;
+        for (int p = 0; p < kDpMaxWorld; ++p)
+            if (p < a.world && p != a.rank)
+                v[p] = ld_packet(local + parity_off + (int64_t)p * a.slot_bytes + i * 16);
+#pragma unroll
+        for (int p = 0; p < kDpMaxWorld; ++p) {
+            if (p < a.world && p != a.rank && v[p].w != tag) {
+                const long long t0 = clock64();
+                do {                                   // bounded: a dead peer must not hang us
+                    v[p] = ld_packet(local + parity_off + (int64_t)p * a.slot_bytes + i * 16);
+                    if (clock64() - t0 > (1ll << 33)) {   // ~4 s
+                        *error = 1u;
+                        break;
+                    }
+                } while (v[p].w != tag);
+            }
+        }
+        DP_TP(3);
+        float s[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int p = 0; p < kDpMaxWorld; ++p) {
+            if (p < a.world) {
+                if (p == a.rank) {
+                    s[0] += f[0]; s[1] += f[1]; s[2] += f[2];
+                } else {
+                    s[0] += __uint_as_float(v[p].x);
+                    s[1] += __uint_as_float(v[p].y);
+                    s[2] += __uint_as_float(v[p].z);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (i * 3 + k < a.n) a.grad[i * 3 + k] = s[k];
+            if (i * 3 + k < a.n_norm) {
+                const float x = s[k] * a.prescale;
                 sq = fmaf(x, x, sq);
             }
         }
     }
+    DP_TP(4);
     sq = licv::warp_sum(sq);
     if ((tid & 31) == 0) slab[tid >> 5] = sq;
     __syncthreads();
     if (tid == 0) {
+#ifdef LICV_TRACE
+        if (blockIdx.x == 0) { DP_TP(5); g_dp_trace_n = trace_slot + 1; }
+#endif
         float t = 0.f;
         for (int w = 0; w < kDpThreads / 32; ++w) t += slab[w];
         a.partial[blockIdx.x] = t;     // no atomics: the norm must be bit-identical on every rank
         __threadfence();
-        if (atomicAdd(ticket1, 1u) == gridDim.x - 1) {   // the last CTA closes the step
-            *ticket1 = 0u;
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {   // the last CTA closes the step
+            *ticket = 0u;
             *step_ctr = step;
         }
     }
 }
 
 }  // namespace
+
+#ifdef LICV_TRACE
+extern "C" int licv_debug_read_dp_trace(long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g_dp_trace, sizeof(long long) * n);
+}
+#endif
 
 extern "C" int64_t licv_dp_region_bytes(int64_t n_floats) {
     if (n_floats < 0) return 0;
@@ -270,21 +309,21 @@ extern "C" int licv_dp_allreduce_adamw(licv_dp_comm* c, float* param, float* gra
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const Layout L = layout_of(c->n);
     DpArgs a;
-    for (int p = 0; p < kDpMaxWorld; ++p) a.peer[p] = p < c->world ? c->region[p] : nullptr;
-    a.local = c->region[c->rank];
+    for (int p = 0; p < kDpMaxWorld; ++p) a.region[p] = p < c->world ? c->region[p] : nullptr;
     a.grad = grad;
     a.n = c->n;            // grad must have room for the padding (n rounded up to 4 floats)
     a.n_norm = n_vec + n_alpha;
+    a.n_packets = L.n_packets;
     a.slot_bytes = L.slot_bytes;
-    a.flags_off = L.flags_off;
     a.ctl_off = L.ctl_off;
     a.rank = c->rank;
     a.world = c->world;
     a.prescale = 1.0f / (float)c->world;
     a.partial = reinterpret_cast<float*>(c->region[c->rank] + L.partial_off);
-    if (int rc = licv::launch_pdl(dp_exchange_kernel, dim3(kDpCtas), dim3(kDpThreads), 0, st, a)) return rc;
+    const int grid = grid_of(L);
+    if (int rc = licv::launch_pdl(dp_exchange_kernel, dim3(grid), dim3(kDpThreads), 0, st, a)) return rc;
     return licv::launch_adamw_after_norm(param, grad, exp_avg, exp_avg_sq, n_vec, n_alpha, lr_vec,
                                          lr_alpha, beta1, beta2, eps, weight_decay, step,
                                          1.0f / (float)c->world, max_grad_norm, norm_out, workspace,
-                                         a.partial, kDpCtas, st);
+                                         a.partial, grid, st);
 }

@@ -208,7 +208,9 @@ int licv_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_
  *   SUM over ranks on return (summed in rank order: bit-identical on every rank); the parameters
  *   are updated with the mean gradient (clip at max_grad_norm, AdamW).  Two launches, no host
  *   synchronisation, replayable from a CUDA graph (the step counter lives in device memory).
- *   world == 1 degenerates to licv_adamw_step.
+ *   world == 1 degenerates to licv_adamw_step.  A region holds two slots per possible source
+ *   rank (16) of 16-byte {3 floats, step tag} packets: about 22 MB for idefics shapes.  Every
+ *   rank must call once per step, with the same step number.
  * ------------------------------------------------------------------------------------------ */
 typedef struct licv_dp_comm licv_dp_comm;
 int64_t licv_dp_region_bytes(int64_t n_floats);

@@ -68,7 +68,7 @@ def test_exchange_region_holds_two_packet_slots_per_source_rank():
         slot = (packets * 16 + 255) // 256 * 256
         assert got >= 2 * 16 * slot + 64
         assert got <= 2 * 16 * slot + 64 + 4096
-        assert got > prev
+        assert got >= prev
         prev = got
 
 

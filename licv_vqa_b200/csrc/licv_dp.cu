@@ -231,6 +231,8 @@ extern "C" int licv_dp_region_alloc(int64_t n_floats, void** region, void* ipc_h
     cudaError_t e = cudaMalloc(&p, (size_t)bytes);
     if (e != cudaSuccess) return (int)e;
     e = cudaMemset(p, 0, (size_t)bytes);
+    // peers write into this region as soon as they hold the handle: the zero tags must be there
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
     if (e != cudaSuccess) {

@@ -1,7 +1,12 @@
-"""Debug: phase timeline of the cluster KD kernel (needs a build with LICV_EXTRA_NVCC_FLAGS=-DLICV_TRACE)."""
+"""Debug: phase timeline of the cluster KD kernel (needs a build with LICV_EXTRA_NVCC_FLAGS=-DLICV_TRACE).
+
+The trace points live in kd_loss_cluster_kernel, so the tensor-memory kernel (the default for
+16-bit logits) is switched off for this process."""
 import ctypes
 import os
 import sys
+
+os.environ["LICV_KD_TMEM"] = "0"
 
 import numpy as np
 import torch

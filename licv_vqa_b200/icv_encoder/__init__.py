@@ -1,4 +1,3 @@
-from .base_icv_encoder import BaseICVEncoder, ICVEncoderOutput
-from .global_icv_encoder import GlobalICVEncoder
+from .encoders import BaseICVEncoder, GlobalICVEncoder, ICVEncoderOutput
 
 __all__ = ["BaseICVEncoder", "ICVEncoderOutput", "GlobalICVEncoder"]

@@ -17,8 +17,7 @@ by index lists computed on the device (`ops.kd_prepare_rows`) - no gathered copi
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from types import SimpleNamespace
-from typing import Any, Optional
+from typing import Any
 
 import torch
 from torch import nn

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import licv_oracle as O
-from tests.util import EPS, load_golden, rel_err
+from tests.util import load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 

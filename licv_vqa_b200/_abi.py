@@ -10,7 +10,8 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "liblicv_b200.so")
+# LICV_LIB: an alternative build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("LICV_LIB") or os.path.join(_PKG, "lib", "liblicv_b200.so")
 
 F32, BF16, F16 = 0, 1, 2
 ROUND_Y, ROUND_NH, ROUND_NY, ROUND_T, ROUND_TEMPERED = 1, 2, 4, 8, 16

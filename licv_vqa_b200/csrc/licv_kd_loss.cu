@@ -377,6 +377,7 @@ extern "C" int licv_kd_loss_fwd_bwd(const void* stu, void* dstu, const void* tea
     a.n_rows = n_rows; a.vocab = vocab; a.stu_stride = stu_stride; a.tea_stride = tea_stride;
     a.round_flags = round_flags;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (kd_stream_plan(vocab, dtype)) return launch_kd_stream(a, dtype, st);
     if (kd_tmem_plan(vocab, dtype, temperature, ce_label != nullptr && !only_hard_loss))
         return launch_kd_tmem(a, dtype, st);
     int C = 0, NV = 0, NT = 0;

@@ -33,6 +33,10 @@ bool kd_cluster_plan(int vocab, int dtype, float temperature, bool kl_and_ce, in
 // (LICV_KD_TMEM=0 disables it)
 bool kd_tmem_plan(int vocab, int dtype, float temperature, bool kl_and_ce);
 int launch_kd_tmem(const KdArgs& a, int dtype, cudaStream_t st);
+// stream kernel (licv_kd_loss_stream.cu): 16-bit logits, 16 377 <= V <= 32 752; TMA-staged rows,
+// sweep D of a row fused with sweep B of the next (LICV_KD_STREAM=0 disables it)
+bool kd_stream_plan(int vocab, int dtype);
+int launch_kd_stream(const KdArgs& a, int dtype, cudaStream_t st);
 int launch_kd_cluster(const KdArgs& a, int dtype, int C, int NV, int NT, cudaStream_t st);
 
 }  // namespace licv

@@ -1,0 +1,1136 @@
+// L-ICV distillation loss, stream kernel: the loss kernel for 16-bit logits of 16k..32k entries
+// (every reference model: idefics-9b V = 32002, idefics2-8b V = 32003).
+//
+// Same arithmetic as licv_kd_loss.cu / licv_kd_loss_cluster.cu (reference icv_src/icv_module.py:
+// 121-134 for the KL, the HF-internal shifted CE consumed at :94-98,115-117, the combine at
+// :100-101,107-119).  What changes against the tensor-memory kernel of round 1 is the SCHEDULE.
+//
+// A KL+CE row needs three element sweeps with two row-wide reductions between them:
+//   B  raw logits -> e_s = 2^(u_s - m), e_t = 2^(u_t - m)  (2 MUFU / element), partition sums
+//   C  e_s, e_t -> p, q, KL terms, w = p q/(q+eps)         (2 MUFU / element), KL_n and W_n
+//   D  e_s, w -> gradient, written to HBM                   (0 MUFU)
+// The SFU pipe (16 MUFU/clk/SM) and HBM (192 KB per row pair) each need ~8 k clocks per 32 k row,
+// so a schedule in which the sweeps of ONE row run back to back alternates between an SFU-bound
+// phase and a memory-bound phase and reaches < 50 % of either.  The fp32 caches of a row pair
+// (2 x 128 KB) fill the SM, so two rows can not be in flight as two CTAs either.  Here the rows are
+// skewed instead: sweep D of row r and sweep B of row r+1 are ONE fused sweep - each thread turns
+// the cache slot of its vector into gradient, stores it, and refills the same slot with the next
+// row's exponentials - so every sweep carries 2 MUFU per element, and
+//   * the raw logits arrive through a ring of shared-memory slots filled by 1-D TMA bulk copies
+//     (cp.async.bulk, SASS UBLKCP) that a dedicated producer warp issues up to 1.5 rows ahead:
+//     no prefetch registers, HBM reads run under both sweeps;
+//   * the packed fp32x2 instructions of sm_100 (FFMA2 / FADD2 / FMUL2) halve the issue slots of
+//     the fp32 arithmetic (round 1: 36.7 thread instructions per element, issue 47 % busy at 46 %
+//     of the roofline);
+//   * the exponentials are taken relative to a CTA-wide reference exponent that is known before
+//     the row arrives - the previous row's log-sum-exp (rows of one model live on the same scale),
+//     for a CTA's first row the maximum of its first 4096 logits - instead of the row's maximum,
+//     which removes the pass that needs the whole row before the first exponential and turns the
+//     softmax reduction into a plain sum; a row whose partition sum leaves [2^-64, 2^120] because
+//     of it is rebuilt from global memory with its exact maxima - a cold path.
+// e_s lives in shared memory (128 KB, thread-private float4 slots), e_t / -kl_w w in tensor memory
+// (256 columns, tcgen05.ld/st = SASS LDTM/STTM), the ring takes the remaining ~96 KB.
+//
+// Not a dense contraction: no tensor cores; bounds are HBM, the SFU pipe and issue slots.
+#include <cstdlib>
+#include <type_traits>
+
+#include "licv_common.cuh"
+#include "licv_kd_loss.cuh"
+#include "licv_kd_rows.cuh"
+
+namespace licv {
+namespace {
+
+constexpr int kST = 512;                  // compute threads (16 warps) + one producer warp group
+constexpr int kBlock = kST + 128;         // the producer warp group: one working lane, registers handed over
+constexpr int kSW = kST / 32;
+constexpr int kChunk = kST * 16;          // bytes of one vector group (512 vectors) of one row
+// One ring slot = one mbarrier = two chunks: (student k, teacher k) of a KL row, or the student
+// chunks (2j, 2j+1) of a row without a teacher.  The second half is one granule longer: a teacher
+// row may sit on another 16-byte phase than its student row.
+constexpr int kSlotBytes = 2 * kChunk + 16;
+constexpr int kMaxSlots = 16;
+constexpr int kPeekMargin = 8;             // octaves added to the maximum of a row's first vector group
+constexpr int kDescRows = 16;             // row descriptors staged in shared memory at a time (power of two)
+constexpr int kSmemBudget = 230400;       // dynamic shared memory (static part: ~1.6 KB)
+
+__host__ __device__ constexpr int stream_slots(int nv) {
+    return (kSmemBudget - nv * 2 * kST * 16) / kSlotBytes > kMaxSlots
+               ? kMaxSlots
+               : (kSmemBudget - nv * 2 * kST * 16) / kSlotBytes;
+}
+
+// ---- mbarrier / bulk-copy helpers ------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+        : "memory");
+    return ok != 0;
+}
+// bounded: a broken pipeline traps (the launch fails) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    int spins = 0;
+    while (!mbar_try(bar, parity)) {
+        if (++spins > 8000) __trap();
+    }
+}
+// 1-D TMA bulk copy global -> shared, completing on an mbarrier.  No L2 cache hint: evict-first
+// measured 5 % slower here (463 vs 441 us at 8192 x 32002 KL+CE rows).
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ uint4 lds128(const void* p) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "r"(smem_u32(p)));
+    return r;
+}
+// the same with 32-bit shared-memory addresses (no generic-pointer arithmetic in the hot loops)
+__device__ __forceinline__ bool mbar_try_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(1000000u)
+        : "memory");
+    return ok != 0;
+}
+// non-blocking: has the phase completed?
+__device__ __forceinline__ bool mbar_test_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    if (mbar_try_a(bar, parity)) return;
+    int spins = 0;
+    while (!mbar_try_a(bar, parity)) {
+        if (++spins > 8000) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds128_a(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void sts128_a(uint32_t addr, float2 a, float2 b) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y)
+                 : "memory");
+}
+// barrier among the compute threads only (the producer warp never joins it)
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kST) : "memory"); }
+
+// ---- packed fp32 pairs -----------------------------------------------------------------------
+template <int DT> __device__ __forceinline__ void unpack2(const uint4& v, float2 (&f)[4]);
+template <> __device__ __forceinline__ void unpack2<LICV_BF16>(const uint4& v, float2 (&f)[4]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        f[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+}
+template <> __device__ __forceinline__ void unpack2<LICV_F16>(const uint4& v, float2 (&f)[4]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+}
+template <int DT> __device__ __forceinline__ uint32_t pack2(float2 f);
+template <> __device__ __forceinline__ uint32_t pack2<LICV_BF16>(float2 f) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(f.x, f.y);
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+template <> __device__ __forceinline__ uint32_t pack2<LICV_F16>(float2 f) {
+    const __half2 p = __floats2half2_rn(f.x, f.y);
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+__device__ __forceinline__ float2 splat(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 as_f2(uint32_t a, uint32_t b) {
+    return make_float2(__uint_as_float(a), __uint_as_float(b));
+}
+
+// 16 bytes that start `d` bytes (even, < 16) into the aligned granule pair (a, b)
+__device__ __forceinline__ uint4 shift_granules(const uint4& a, const uint4& b, uint32_t d) {
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const uint32_t bits = (d & 3u) * 8u;
+    uint4 r;
+    switch (d >> 2) {   // the same for every thread of the CTA: no divergence
+        case 0:
+            r = make_uint4(__funnelshift_r(w[0], w[1], bits), __funnelshift_r(w[1], w[2], bits),
+                           __funnelshift_r(w[2], w[3], bits), __funnelshift_r(w[3], w[4], bits));
+            break;
+        case 1:
+            r = make_uint4(__funnelshift_r(w[1], w[2], bits), __funnelshift_r(w[2], w[3], bits),
+                           __funnelshift_r(w[3], w[4], bits), __funnelshift_r(w[4], w[5], bits));
+            break;
+        case 2:
+            r = make_uint4(__funnelshift_r(w[2], w[3], bits), __funnelshift_r(w[3], w[4], bits),
+                           __funnelshift_r(w[4], w[5], bits), __funnelshift_r(w[5], w[6], bits));
+            break;
+        default:
+            r = make_uint4(__funnelshift_r(w[3], w[4], bits), __funnelshift_r(w[4], w[5], bits),
+                           __funnelshift_r(w[5], w[6], bits), __funnelshift_r(w[6], w[7], bits));
+            break;
+    }
+    return r;
+}
+
+#ifdef LICV_TRACE
+// debug build only: per CTA {start ns, end ns, smid, rows} of the last launch
+__device__ unsigned long long g_scta[256 * 4];
+__device__ long long g_sphase[2 * 16 * 8];  // CTAs 0 and 5, per warp: clocks in {red1, C, red2, setup, sweep, tail, rows}
+#define LICV_STAMP(i) do { const long long now_ = clock64(); if (it >= 2) ph_[i] += now_ - tlast_; tlast_ = now_; } while (0)
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#else
+#define LICV_STAMP(i) do { } while (0)
+#endif
+
+// clamp(ceil(x)) as a float: the reference exponent for logits around x (x = max or lse, in octaves)
+__device__ __forceinline__ float ref_of(float octaves) {
+    return fminf(fmaxf(ceilf(octaves), -1.0e6f), 1.0e6f);          // -inf -> -1e6, NaN -> -1e6
+}
+// a partition sum taken against a guessed reference is usable: finite, not flushed away
+__device__ __forceinline__ bool z_usable(float z) { return z >= 5.4e-20f && z <= 1.3e36f; }
+
+template <int DT, int NV>
+__global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
+    constexpr int EPV = 8;
+    constexpr int EB = 2;
+    constexpr int kSlots = stream_slots(NV);
+    constexpr int kStep = kST * EPV;
+    constexpr int kCols = tmem_cols(kST, NV);
+    static_assert(Fmt<DT>::kBytes == 2, "16-bit logits only");
+    static_assert(kSlots >= 4 && NV % 2 == 0, "ring too small / odd vector count");
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4* const cs = reinterpret_cast<float4*>(smem);                 // [NV * 2][kST]: e_s, fp32
+    unsigned char* const ring = smem + (size_t)NV * 2 * kST * 16;       // [kSlots][kSlotBytes]
+    __shared__ __align__(8) uint64_t full[kMaxSlots], empty[kMaxSlots];
+    __shared__ __align__(16) float4 slab[4][kSW];                       // reduction partials, rotating
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_tot[2 * kSW];
+    __shared__ int s_last;
+    __shared__ __align__(16) uint32_t s_desc[kDescRows][16];          // row descriptors, see fill_desc
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < kSlots; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kSW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&s_tmem)),
+                     "n"(kCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    pdl_launch_dependents();
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    pdl_wait();   // the previous kernel's logits / row lists are visible from here on
+#ifdef LICV_TRACE
+    if (tid == 0 && blockIdx.x < 256) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_scta[blockIdx.x * 4] = globaltimer_ns();
+        g_scta[blockIdx.x * 4 + 2] = smid;
+    }
+#endif
+
+    const float T = a.temperature;
+    const float inv_t = 1.0f / T;
+    const bool round_tempered = (a.round_flags & LICV_ROUND_TEMPERED) && T != 1.0f;
+    const int64_t n_kl = a.counts ? (int64_t)a.counts[0] : a.n_kl;
+    const int64_t n_ce = a.counts ? (int64_t)a.counts[1] : a.n_ce;
+    const bool use_kl = !a.only_hard_loss;
+    const bool use_ce = a.ce_label != nullptr;
+    const int V = a.vocab;
+    const int64_t G = gridDim.x;
+
+    auto fetch_tr = [&](int64_t r) -> int {
+        if (!use_kl || r >= a.n_rows) return -1;
+        return a.kl_tea_row ? a.kl_tea_row[r] : (int)r;
+    };
+    auto fetch_lab = [&](int64_t r) -> int {
+        if (!use_ce || r >= a.n_rows) return kLabNone;
+        const int64_t l = a.ce_label[r];
+        return (l < -100 || l > 0x7fffffff) ? kLabBad : (int)l;
+    };
+    auto x_row = [&](int64_t r) { return static_cast<const char*>(a.stu) + (size_t)r * a.stu_stride * EB; };
+    auto t_row = [&](int tr) { return static_cast<const char*>(a.tea) + (size_t)tr * a.tea_stride * EB; };
+    auto g_row = [&](int64_t r) { return static_cast<char*>(a.dstu) + (size_t)r * a.stu_stride * EB; };
+    auto phase16 = [](const void* p) { return (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u); };
+
+    // =========================================================================================
+    // producer warp group: one lane walks this CTA's rows in the order the compute warps consume
+    // them and keeps the ring full; the group's registers go to the compute warps.  Chunk
+    // (row, k, stream) = the 512 16-byte vectors k*512 .. of the row, in the STUDENT row's 16-byte
+    // phase (the first / last vector of a row may be partial: whole granules are copied and the
+    // elements outside the row are masked where consumed).
+    // =========================================================================================
+    if (warp >= kSW) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        if (warp == kSW && lane == 0) {
+            uint32_t pslot = 0, ppar = 1;      // parity to wait for on `empty`: a fresh barrier passes 1
+            // two bulk copies into one slot, completing on its one barrier
+            auto emit2 = [&](const char* src0, int64_t bytes0, const char* src1, uint32_t dst_off1, int64_t bytes1) {
+                mbar_wait_bounded(&empty[pslot], ppar);
+                const uint32_t nb0 = bytes0 > 0 ? (uint32_t)bytes0 : 0u, nb1 = bytes1 > 0 ? (uint32_t)bytes1 : 0u;
+                unsigned char* dst = ring + (size_t)pslot * kSlotBytes;
+                mbar_arrive_tx(&full[pslot], nb0 + nb1);
+                if (nb0) bulk_g2s(dst, src0, nb0, &full[pslot]);
+                if (nb1) bulk_g2s(dst + kChunk + dst_off1, src1, nb1, &full[pslot]);
+                if (++pslot == (uint32_t)kSlots) {
+                    pslot = 0;
+                    ppar ^= 1u;
+                }
+            };
+            for (int64_t r = blockIdx.x; r < a.n_rows; r += G) {
+                const int tr = fetch_tr(r);
+                const int lab = fetch_lab(r);
+                if (tr < 0 && lab == kLabNone) continue;
+                const char* xr = x_row(r);
+                const uint32_t ph = phase16(xr);
+                const char* xb = xr - ph;                                          // first granule
+                const int64_t xspan = ((int64_t)ph + (int64_t)V * EB + 15) & ~(int64_t)15;
+                auto s_bytes = [&](int k) -> int64_t {
+                    const int64_t left = xspan - (int64_t)k * kChunk;
+                    return left < kChunk ? left : kChunk;
+                };
+                if (tr >= 0) {
+                    const char* tp = t_row(tr);
+                    const char* ta = tp - ph;   // address of the teacher element paired with xb's first
+                    const uint32_t d = phase16(ta);
+                    const char* tlo = tp - phase16(tp);
+                    const char* thi = tp + (int64_t)V * EB;
+                    thi += (16u - phase16(thi)) & 15u;
+#pragma unroll 1
+                    for (int k = 0; k < NV; ++k) {
+                        const int64_t off = (int64_t)k * kChunk;
+                        const char* base = ta - d + off;                            // 16-byte aligned
+                        const char* end = base + kChunk + (d ? 16 : 0);
+                        const char* s0 = base < tlo ? tlo : base;
+                        const char* e0 = end > thi ? thi : end;
+                        emit2(xb + off, s_bytes(k), s0, (uint32_t)(s0 - base), e0 - s0);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int k = 0; k < NV; k += 2)
+                        emit2(xb + (int64_t)k * kChunk, s_bytes(k), xb + (int64_t)(k + 1) * kChunk, 0u, s_bytes(k + 1));
+                }
+            }
+        }
+    } else {
+        // =====================================================================================
+        // compute warps
+        // =====================================================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        const float kl_w = use_kl ? a.grad_scale * T / (float)n_kl : 0.f;
+        const float ce_w = use_ce ? a.grad_scale * (a.only_hard_loss ? 1.0f : a.hard_loss_weight) /
+                                        (float)n_ce
+                                  : 0.f;
+        const float eps = a.kl_eps;
+        float* row_kl = a.row_loss;
+        float* row_ce = a.row_loss + a.n_rows;
+        // this thread's 64 columns of tensor memory: lane quarter of the warp, column group of the warp
+        const uint32_t tcol = s_tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * (NV * 8));
+        const uint32_t ring_a = smem_u32(ring) + tid * 16, cs_a = smem_u32(cs) + tid * 16;
+        const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
+        const uint32_t slab_a = smem_u32(slab);
+
+        // CTA-wide sums of up to three values: warp shuffles, 16 partials through shared memory, one
+        // barrier; the slabs rotate so that a fast warp's next partial never meets a slow reader
+        uint32_t slab_i = 0;
+        auto cta_sum3 = [&](float x, float y, float z) -> float4 {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                x += __shfl_xor_sync(0xffffffffu, x, o);
+                y += __shfl_xor_sync(0xffffffffu, y, o);
+                z += __shfl_xor_sync(0xffffffffu, z, o);
+            }
+            const uint32_t base = slab_a + slab_i * (kSW * 16);
+            slab_i = (slab_i + 1) & 3u;
+            if (lane == 0)
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(base + warp * 16), "f"(x), "f"(y),
+                             "f"(z), "f"(0.f)
+                             : "memory");
+            compute_sync();
+            const uint4 p = lds128_a(base + (lane & (kSW - 1)) * 16);
+            x = __uint_as_float(p.x);
+            y = __uint_as_float(p.y);
+            z = __uint_as_float(p.z);
+#pragma unroll
+            for (int o = kSW / 2; o > 0; o >>= 1) {
+                x += __shfl_xor_sync(0xffffffffu, x, o);
+                y += __shfl_xor_sync(0xffffffffu, y, o);
+                z += __shfl_xor_sync(0xffffffffu, z, o);
+            }
+            return make_float4(x, y, z, 0.f);
+        };
+        auto cta_max2 = [&](float x, float y) -> float2 {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+                y = fmaxf(y, __shfl_xor_sync(0xffffffffu, y, o));
+            }
+            const uint32_t base = slab_a + slab_i * (kSW * 16);
+            slab_i = (slab_i + 1) & 3u;
+            if (lane == 0)
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(base + warp * 16), "f"(x), "f"(y),
+                             "f"(0.f), "f"(0.f)
+                             : "memory");
+            compute_sync();
+            const uint4 p = lds128_a(base + (lane & (kSW - 1)) * 16);
+            x = __uint_as_float(p.x);
+            y = __uint_as_float(p.y);
+#pragma unroll
+            for (int o = kSW / 2; o > 0; o >>= 1) {
+                x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+                y = fmaxf(y, __shfl_xor_sync(0xffffffffu, y, o));
+            }
+            return make_float2(x, y);
+        };
+        // Row descriptors: everything the sweeps need to know about a row is worked out ONCE, by one
+        // thread per row, kDescRows rows at a time, and read back with three 16-byte loads - the
+        // per-row bookkeeping (pointers, phases, flags, the label logit) executed by all 16 warps was
+        // ~12 of 41 thread instructions per element in the first version of this kernel.
+        //   word 0 flags, 1 teacher row, 2 label, 3 student phase | teacher offset << 8,
+        //   4-5 student row, 6-7 gradient row (0 = none), 8 label logit, 9 vector groups wholly
+        //   inside the row, 10-11 row index
+        constexpr uint32_t F_VALID = 1, F_KL = 2, F_CE = 4, F_CET = 8, F_RND = 16, F_GVEC = 32;
+        const uint32_t desc_a = smem_u32(s_desc);
+        auto fill_desc = [&](int it0) {
+            compute_sync();
+            if (tid < kDescRows) {
+                const int64_t r = (int64_t)blockIdx.x + (int64_t)(it0 + tid) * G;
+                uint32_t flags = 0, ph_nd = 0;
+                int tr = -1, lab = kLabNone, kfull = 0;
+                const char* xr = nullptr;
+                char* gp = nullptr;
+                float xl = 0.f;
+                if (r < a.n_rows) {
+                    tr = fetch_tr(r);
+                    lab = fetch_lab(r);
+                    const bool kl = tr >= 0, ce = lab != kLabNone;
+                    xr = x_row(r);
+                    const uint32_t ph = phase16(xr);
+                    gp = a.dstu ? g_row(r) : nullptr;
+                    flags = F_VALID | (kl ? F_KL : 0u) | (ce ? F_CE : 0u) | (kl && ce && T != 1.0f ? F_CET : 0u) |
+                            (kl && round_tempered ? F_RND : 0u) | (gp && phase16(gp) == ph ? F_GVEC : 0u);
+                    const uint32_t nd = kl ? ((phase16(t_row(tr)) - ph) & 15u) : 0u;
+                    ph_nd = ph | (nd << 8);
+                    // the label logit, read before the gradient may overwrite the row in place
+                    if (ce && lab >= 0 && lab < V) xl = load_elem<DT>(xr, lab);
+                    kfull = (V + (int)(ph / EB)) / kStep;
+                }
+                uint32_t* d = s_desc[tid];
+                d[0] = flags; d[1] = (uint32_t)tr; d[2] = (uint32_t)lab; d[3] = ph_nd;
+                *reinterpret_cast<const char**>(d + 4) = xr;
+                *reinterpret_cast<char**>(d + 6) = gp;
+                d[8] = __float_as_uint(xl); d[9] = (uint32_t)kfull;
+                *reinterpret_cast<int64_t*>(d + 10) = r;
+            }
+            compute_sync();
+        };
+        uint32_t slot = 0, par = 0;  // ring position of the next chunk to consume
+        auto adv = [&]() {
+            if (++slot == (uint32_t)kSlots) {
+                slot = 0;
+                par ^= 1u;
+            }
+        };
+
+        // ---- state of the row whose caches are complete (cur) and of the row being built (nxt) ----
+        uint32_t c_flags = 0;
+        int c_tr = -1, c_lab = kLabNone, c_j0 = 0, c_kfull = 0;
+        const char* c_xr = nullptr;
+        char* c_gp = nullptr;
+        int64_t c_r = -1;
+        float x_lab = 0.f;                         // cur: label logit
+        float zs = 0.f, zt = 0.f, zc = 0.f;        // cur: this thread's partition sums
+        float ref_s = 0.f, ref_t = 0.f, ref_c = 0.f;   // cur: reference exponents of the three streams
+        // where the logits of this CTA's rows live (in logit units; NaN = not known yet)
+        float hint_s = __int_as_float(0x7fc00000), hint_t = hint_s;
+        int it = 0;                  // ordinal of nxt among this CTA's rows
+        fill_desc(0);
+#ifdef LICV_TRACE
+        long long ph_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long tlast_ = clock64();
+#endif
+
+        while (true) {
+            const bool c_valid = c_flags & F_VALID;
+            const bool c_kl = c_flags & F_KL, c_ce = c_flags & F_CE;
+            const bool c_work = c_flags & (F_KL | F_CE);
+            const bool c_cet = c_flags & F_CET;           // CE on raw logits next to a tempered KL
+            // nxt: its descriptor
+            const uint32_t nda = desc_a + (uint32_t)(it & (kDescRows - 1)) * 64u;
+            const uint4 nd0 = lds128_a(nda), nd1 = lds128_a(nda + 16), nd2 = lds128_a(nda + 32);
+            const uint32_t n_flags = nd0.x;
+            const int n_tr = (int)nd0.y, n_lab = (int)nd0.z;
+            const bool n_valid = n_flags & F_VALID;
+            const bool nx_kl = n_flags & F_KL;
+            const bool n_work = n_flags & (F_KL | F_CE);
+            const bool n_cet = n_flags & F_CET;
+
+            // ---------------------------------------------------------------------------------
+            // cur: reduction 1, sweep C, reduction 2
+            // ---------------------------------------------------------------------------------
+            float A = 0.f, kl_row = 0.f, ce_row = 0.f, cq = 0.f;
+            LICV_STAMP(5);
+            if (c_work) {
+                const float it_c = c_kl ? inv_t : 1.0f;
+                const bool rnd_c = c_flags & F_RND;
+                const float c_c = rnd_c ? kLog2e : kLog2e * it_c;        // u = logit * c_c
+                float4 tot = cta_sum3(zs, zt, zc);
+                LICV_STAMP(0);
+                const bool bad = !z_usable(tot.x) || (c_kl && !z_usable(tot.y)) || (c_cet && !z_usable(tot.z));
+                if (bad) {
+                    // ---- cold path: the guessed reference was off by more than the window (or the row
+                    //      holds inf / NaN): rebuild the caches from global memory with exact maxima
+                    const char* tp = c_kl ? t_row(c_tr) : nullptr;
+                    const uint32_t dph = c_kl ? ((phase16(tp) - phase16(c_xr)) & 15u) : 0u;
+                    const int t_align = dph == 0 ? 16 : (int)(dph & (0u - dph));
+                    RawMax<DT> mxs, mxt;
+#pragma unroll 1
+                    for (int k = 0; k < NV; ++k) {
+                        uint4 v[1];
+                        load_row_vecs<DT, 1>(v, c_xr, c_j0 + k * kStep, kStep, V, 16, lane);
+                        mask_row_vecs<DT, 1>(v, c_j0 + k * kStep, kStep, V, lane);
+                        mxs.add(v[0]);
+                        if (c_kl) {
+                            load_row_vecs<DT, 1>(v, tp, c_j0 + k * kStep, kStep, V, t_align, lane);
+                            mask_row_vecs<DT, 1>(v, c_j0 + k * kStep, kStep, V, lane);
+                            mxt.add(v[0]);
+                        }
+                    }
+                    const float2 mx = cta_max2(mxs.get(), c_kl ? mxt.get() : 0.f);
+                    auto tempered_max = [&](float m) {
+                        m *= it_c;
+                        return rnd_c ? Fmt<DT>::round(m) : m;
+                    };
+                    ref_s = ref_of(tempered_max(mx.x) * kLog2e);
+                    ref_t = ref_of(tempered_max(mx.y) * kLog2e);
+                    ref_c = ref_of(mx.x * kLog2e);
+                    zs = zt = zc = 0.f;
+#pragma unroll 1
+                    for (int k = 0; k < NV; ++k) {
+                        uint4 v[1];
+                        float x[EPV];
+                        load_row_vecs<DT, 1>(v, c_xr, c_j0 + k * kStep, kStep, V, 16, lane);
+                        mask_row_vecs<DT, 1>(v, c_j0 + k * kStep, kStep, V, lane);
+                        unpack<DT>(v[0], x);
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e) {
+                            if (c_cet) zc += ex2(fmaf(x[e], kLog2e, -ref_c));
+                            float u = x[e];
+                            if (rnd_c) u = Fmt<DT>::round(u * it_c);
+                            x[e] = ex2(fmaf(u, c_c, -ref_s));
+                            zs += x[e];
+                        }
+                        cs[(k * 2) * kST + tid] = make_float4(x[0], x[1], x[2], x[3]);
+                        cs[(k * 2 + 1) * kST + tid] = make_float4(x[4], x[5], x[6], x[7]);
+                        if (c_kl) {
+                            load_row_vecs<DT, 1>(v, tp, c_j0 + k * kStep, kStep, V, t_align, lane);
+                            mask_row_vecs<DT, 1>(v, c_j0 + k * kStep, kStep, V, lane);
+                            unpack<DT>(v[0], x);
+#pragma unroll
+                            for (int e = 0; e < EPV; ++e) {
+                                float u = x[e];
+                                if (rnd_c) u = Fmt<DT>::round(u * it_c);
+                                x[e] = ex2(fmaf(u, c_c, -ref_t));
+                                zt += x[e];
+                            }
+                            tmem_st8(tcol + k * 8, x);
+                        }
+                    }
+                    tmem_wait_st();
+                    tot = cta_sum3(zs, zt, zc);
+                }
+                // where this row's logits were: the guess for the next row's references
+                const float lz_s = lg2(tot.x);
+                const float inv_c = (c_kl ? T : 1.0f) * kLn2;             // octaves -> logit units
+                hint_s = (ref_s + lz_s) * inv_c;
+                if (c_kl) hint_t = (ref_t + lg2(tot.y)) * inv_c;
+                const float fs = rcp(tot.x);                              // q = e_s * fs
+                float W = 0.f;
+                if (c_kl) {
+                    // ---- sweep C: KL terms and w; -kl_w w replaces e_t in tensor memory ------------
+                    const float ft = rcp(tot.y);                          // p = e_t * ft
+                    const float2 fs2 = splat(fs), ft2 = splat(ft), eps2 = splat(eps), nkw2 = splat(-kl_w);
+                    float2 klp2 = splat(0.f), wp2 = splat(0.f);
+                    const bool keep = a.dstu != nullptr;
+                    // software pipeline: the cache reads of vector k+1 are in flight under the
+                    // arithmetic of vector k (four warps per scheduler do not hide them otherwise)
+                    uint32_t tbA[8], tbB[8];
+                    uint4 eA0, eA1, eB0, eB1;
+                    auto c_load = [&](int k, uint32_t (&tb)[8], uint4& e0, uint4& e1) {
+                        tmem_ld8_issue(tcol + k * 8, tb);
+                        e0 = lds128_a(cs_a + (k * 2) * kST * 16);
+                        e1 = lds128_a(cs_a + (k * 2 + 1) * kST * 16);
+                    };
+                    auto c_math = [&](int k, uint32_t (&tb)[8], const uint4& e0, const uint4& e1) {
+                        const float2 es[4] = {as_f2(e0.x, e0.y), as_f2(e0.z, e0.w), as_f2(e1.x, e1.y),
+                                              as_f2(e1.z, e1.w)};
+                        float nw[8];
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const float2 q = __fmul2_rn(es[h], fs2);
+                            const float2 p = __fmul2_rn(as_f2(tb[2 * h], tb[2 * h + 1]), ft2);
+                            const float2 qe = __fadd2_rn(q, eps2);
+                            const float2 rq = make_float2(rcp(qe.x), rcp(qe.y));
+                            const float2 ratio = __fmul2_rn(__fadd2_rn(p, eps2), rq);
+                            // ln(p+eps) - ln(q+eps) = ln((p+eps)/(q+eps))
+                            const float2 lr = make_float2(lg2(ratio.x), lg2(ratio.y));
+                            klp2 = __ffma2_rn(p, lr, klp2);
+                            const float2 w = __fmul2_rn(__fmul2_rn(p, q), rq);
+                            wp2 = __fadd2_rn(wp2, w);
+                            const float2 n = __fmul2_rn(w, nkw2);
+                            nw[2 * h] = n.x;
+                            nw[2 * h + 1] = n.y;
+                        }
+                        if (keep) tmem_st8(tcol + k * 8, nw);
+                    };
+                    c_load(0, tbA, eA0, eA1);
+#pragma unroll 1
+                    for (int k = 0; k < NV; k += 2) {
+                        tmem_ld_wait(tbA);
+                        c_load(k + 1, tbB, eB0, eB1);
+                        c_math(k, tbA, eA0, eA1);
+                        tmem_ld_wait(tbB);
+                        if (k + 2 < NV) c_load(k + 2, tbA, eA0, eA1);
+                        c_math(k + 1, tbB, eB0, eB1);
+                    }
+                    tmem_wait_st();
+                    LICV_STAMP(1);
+                    const float4 r2 = cta_sum3(klp2.x + klp2.y, wp2.x + wp2.y, 0.f);
+                    LICV_STAMP(2);
+                    kl_row = r2.x * kLn2;
+                    W = r2.y;
+                }
+                const float ce_on = c_ce ? ce_w : 0.f;
+                if (c_cet) {
+                    A = fs * kl_w * W;
+                    cq = ce_on * rcp(tot.z);                            // ce_w softmax(x) = 2^(u - ref_c) cq
+                } else {
+                    A = fs * fmaf(kl_w, W, ce_on);                      // c_kl false: W = 0 -> fs * ce_w
+                }
+                if (tid == 0 && c_ce) {
+                    const bool lab_ok = c_lab >= 0 && c_lab < V;
+                    // an out-of-range label is an error in torch; poison the loss instead
+                    const float lse = c_cet ? (ref_c + lg2(tot.z)) * kLn2 : (ref_s + lz_s) * kLn2;
+                    ce_row = lab_ok ? lse - x_lab : __int_as_float(0x7fc00000);
+                }
+            }
+
+            if (!c_valid && !n_valid) break;
+
+            // ---------------------------------------------------------------------------------
+            // fused sweep: D(cur) - gradient out of the caches - and B(nxt) - the next row's
+            // exponentials into the same cache slots
+            // ---------------------------------------------------------------------------------
+            char* const gp = c_gp;
+            const bool g_vec = c_flags & F_GVEC;
+            const float2 A2 = splat(A);
+            const float ce_on = c_ce ? ce_w : 0.f;
+            const float mc_cur = ref_c;          // cur's raw-logit reference (D of a tempered KL + CE row)
+
+            const char* n_xr = reinterpret_cast<const char*>(((uint64_t)nd1.y << 32) | nd1.x);
+            const uint32_t n_ph = nd0.w & 0xffu;
+            const int n_j0 = tid * EPV - (int)(n_ph / EB);
+            const float it_row = nx_kl ? inv_t : 1.0f;
+            const bool rnd_row = n_flags & F_RND;
+            const float c_row = rnd_row ? kLog2e : kLog2e * it_row;
+            const uint32_t n_d = nd0.w >> 8;     // byte offset of the teacher data inside its slots
+
+            // ---- references of nxt: the previous rows' log-sum-exp, or a look at the first chunks ----
+            float nref_s = 0.f, nref_t = 0.f, nref_c = 0.f;
+            if (n_work) {
+                if (!(hint_s == hint_s) || (nx_kl && !(hint_t == hint_t))) {
+                    // nothing known yet: maxima of the first vector group of each stream (the chunks
+                    // are only looked at here; the sweep below consumes them)
+                    mbar_wait_a(full_a + slot * 8, par);
+                    uint4 v = lds128_a(ring_a + slot * kSlotBytes);
+                    v = mask_vec<DT>(v, n_j0, V);
+                    RawMax<DT> ms_, mt_;
+                    ms_.add(v);
+                    if (nx_kl) {
+                        v = lds128_a(ring_a + slot * kSlotBytes + kChunk);
+                        v = mask_vec<DT>(v, n_j0 - (int)(n_d / EB), V);    // that half is on the teacher's phase
+                        mt_.add(v);
+                    }
+                    const float2 mx = cta_max2(ms_.get(), mt_.get());
+                    const float mg = (float)kPeekMargin / kLog2e * (nx_kl ? T : 1.0f);   // margin in logit units
+                    if (!(hint_s == hint_s)) hint_s = mx.x + mg;
+                    if (nx_kl && !(hint_t == hint_t)) hint_t = mx.y + mg;
+                }
+                nref_s = ref_of(hint_s * it_row * kLog2e);
+                nref_t = ref_of(hint_t * it_row * kLog2e);
+                nref_c = ref_of(hint_s * kLog2e);
+            }
+            float2 zs2 = splat(0.f), zt2 = splat(0.f), zc2 = splat(0.f);
+
+            // ---- fast variants: a KL row follows a KL row with the teacher on the student's 16-byte
+            //      phase (MODE 1), or a CE-only row follows a CE-only row (MODE 2); the gradient goes
+            //      out as whole vectors, no rounding of tempered logits.  Everything else (first and
+            //      last sweep, rows in no loss, mixed neighbours, T != 1 with CE, teacher rows on
+            //      another phase) takes the generic loop below.
+            const bool d_fast = gp && g_vec && c_work && !c_cet;
+            const bool b_plain = n_work && !rnd_row && !n_cet;
+            const int n_kfull = (int)nd2.y;
+            const int mode = (d_fast && b_plain && c_kl && nx_kl && n_d == 0) ? 1
+                             : (d_fast && b_plain && !c_kl && !nx_kl)        ? 2
+                                                                             : 0;
+            auto fast_sweep = [&](auto mode_tag) {
+                constexpr int MODE = decltype(mode_tag)::value;
+                const float2 c2 = splat(c_row), nms = splat(-nref_s), nmt = splat(-nref_t);
+                // label relative to this thread's first element; never matches when there is none
+                int lab_rel = (c_ce && c_lab >= 0) ? c_lab - c_j0 : -1;
+                char* gk = gp + (int64_t)c_j0 * EB;
+                // vector groups [1, k_end) lie wholly inside both rows for every thread
+                const int k_end = min(c_kfull, n_kfull);
+                struct Regs {
+                    uint4 raw_s, raw_t, e0, e1;
+                    uint32_t wv[8];
+                    uint32_t ea_s;
+                };
+                Regs ra, rb;
+                // every load of vector group k: raw logits out of the ring, the cache slots of cur.
+                // The slot's barrier was probed one step earlier (`ready`): its latency is off the path.
+                bool ready = false;
+                auto probe = [&]() { ready = mbar_test_a(full_a + slot * 8, par); };
+                auto load = [&](int k, Regs& r) {
+                    if (MODE == 1 || (k & 1) == 0) {
+                        if (!ready) mbar_wait_a(full_a + slot * 8, par);
+                    }
+                    const uint32_t sa = ring_a + slot * kSlotBytes;
+                    r.ea_s = empty_a + slot * 8;
+                    if (MODE == 1) {
+                        r.raw_s = lds128_a(sa);
+                        r.raw_t = lds128_a(sa + kChunk);
+                        adv();
+                        tmem_ld8_issue(tcol + k * 8, r.wv);
+                    } else {
+                        r.raw_s = lds128_a(sa + (k & 1) * kChunk);
+                        if (k & 1) adv();
+                    }
+                    r.e0 = lds128_a(cs_a + (k * 2) * kST * 16);
+                    r.e1 = lds128_a(cs_a + (k * 2 + 1) * kST * 16);
+                };
+                auto step = [&](int k, Regs& r, Regs& rn) {
+                    const bool edge = k == 0 || k >= k_end;
+                    if (k + 1 < NV && (MODE == 1 || (k & 1))) probe();   // the next slot's barrier
+                    // ---- D(cur) -------------------------------------------------------------------------
+                    float2 g[4];
+                    if (MODE == 1) {
+                        tmem_ld_wait(r.wv);
+                        g[0] = __ffma2_rn(as_f2(r.e0.x, r.e0.y), A2, as_f2(r.wv[0], r.wv[1]));
+                        g[1] = __ffma2_rn(as_f2(r.e0.z, r.e0.w), A2, as_f2(r.wv[2], r.wv[3]));
+                        g[2] = __ffma2_rn(as_f2(r.e1.x, r.e1.y), A2, as_f2(r.wv[4], r.wv[5]));
+                        g[3] = __ffma2_rn(as_f2(r.e1.z, r.e1.w), A2, as_f2(r.wv[6], r.wv[7]));
+                    } else {
+                        g[0] = __fmul2_rn(as_f2(r.e0.x, r.e0.y), A2);
+                        g[1] = __fmul2_rn(as_f2(r.e0.z, r.e0.w), A2);
+                        g[2] = __fmul2_rn(as_f2(r.e1.x, r.e1.y), A2);
+                        g[3] = __fmul2_rn(as_f2(r.e1.z, r.e1.w), A2);
+                    }
+                    if ((unsigned)lab_rel < (unsigned)EPV) {
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            if (lab_rel == 2 * h) g[h].x -= ce_on;
+                            if (lab_rel == 2 * h + 1) g[h].y -= ce_on;
+                        }
+                    }
+                    bool vec_store = true;
+                    if (edge) {
+                        const int jwk = c_j0 + k * kStep - lane * EPV;
+                        vec_store = jwk >= 0 && jwk + 32 * EPV <= V;
+                    }
+                    if (vec_store) {
+                        st_vec(reinterpret_cast<uint4*>(gk),
+                               make_uint4(pack2<DT>(g[0]), pack2<DT>(g[1]), pack2<DT>(g[2]), pack2<DT>(g[3])));
+                    } else {
+                        const float gr[EPV] = {g[0].x, g[0].y, g[1].x, g[1].y, g[2].x, g[2].y, g[3].x, g[3].y};
+                        store_row_vec<DT>(gp, c_j0 + k * kStep, V, true, gr);
+                    }
+                    // ---- B(nxt): raw logits out of the ring registers, slots handed back --------------
+                    if (edge) {
+                        const int jwk = n_j0 + k * kStep - lane * EPV;
+                        if (!(jwk >= 0 && jwk + 32 * EPV <= V)) {
+                            r.raw_s = mask_vec<DT>(r.raw_s, n_j0 + k * kStep, V);
+                            if (MODE == 1) r.raw_t = mask_vec<DT>(r.raw_t, n_j0 + k * kStep, V);
+                        }
+                    }
+                    float2 xs[4], xt[4];
+                    unpack2<DT>(r.raw_s, xs);
+                    if (MODE == 1) unpack2<DT>(r.raw_t, xt);
+                    if (MODE == 1 || (k & 1)) {                         // the slot may be refilled
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_a(r.ea_s);
+                    }
+                    // ---- the next vector's loads, in flight under this vector's exponentials ------------
+                    if (k + 1 < NV) load(k + 1, rn);
+                    {
+                        float2 ev[4];
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const float2 u = __ffma2_rn(xs[h], c2, nms);
+                            ev[h] = make_float2(ex2(u.x), ex2(u.y));
+                            zs2 = __fadd2_rn(zs2, ev[h]);
+                        }
+                        sts128_a(cs_a + (k * 2) * kST * 16, ev[0], ev[1]);
+                        sts128_a(cs_a + (k * 2 + 1) * kST * 16, ev[2], ev[3]);
+                    }
+                    if (MODE == 1) {
+                        float ev[8];
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const float2 u = __ffma2_rn(xt[h], c2, nmt);
+                            const float2 e = make_float2(ex2(u.x), ex2(u.y));
+                            zt2 = __fadd2_rn(zt2, e);
+                            ev[2 * h] = e.x;
+                            ev[2 * h + 1] = e.y;
+                        }
+                        tmem_st8(tcol + k * 8, ev);
+                    }
+                    lab_rel -= kStep;
+                    gk += (int64_t)kStep * EB;
+                };
+                load(0, ra);
+#pragma unroll 1
+                for (int k = 0; k < NV; k += 2) {
+                    step(k, ra, rb);
+#ifdef LICV_KD_LOCKSTEP
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + (warp & 3)) : "memory");
+#endif
+                    step(k + 1, rb, ra);
+#ifdef LICV_KD_LOCKSTEP
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + (warp & 3)) : "memory");
+#endif
+                }
+            };
+            LICV_STAMP(3);
+            if (mode == 1) {
+                fast_sweep(std::integral_constant<int, 1>{});
+            } else if (mode == 2) {
+                fast_sweep(std::integral_constant<int, 2>{});
+            } else {
+#pragma unroll 1
+                for (int k = 0; k < NV; ++k) {
+                    // ---- issue every load of this vector first -----------------------------------------
+                    uint4 raw_s = make_uint4(0, 0, 0, 0), raw_t = make_uint4(0, 0, 0, 0), raw_t2 = raw_t;
+                    uint32_t bar_s = 0;
+                    bool release = false;        // this vector is the last reader of its slot
+                    if (n_work) {
+                        bar_s = empty_a + slot * 8;
+                        const uint32_t sa = ring_a + slot * kSlotBytes;
+                        if (nx_kl) {
+                            mbar_wait_a(full_a + slot * 8, par);
+                            raw_s = lds128_a(sa);
+                            raw_t = lds128_a(sa + kChunk);
+                            if (n_d) raw_t2 = lds128_a(sa + kChunk + 16);
+                            release = true;
+                        } else {
+                            if ((k & 1) == 0) mbar_wait_a(full_a + slot * 8, par);
+                            raw_s = lds128_a(sa + (k & 1) * kChunk);
+                            release = k & 1;
+                        }
+                        if (release) adv();
+                    }
+                    const bool d_grad = gp && c_work, d_zero = gp && !c_work;
+                    float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
+                    uint32_t wv[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                    if (d_grad) {
+                        if (c_kl) tmem_ld8_issue(tcol + k * 8, wv);
+                        e0 = cs[(k * 2) * kST + tid];
+                        e1 = cs[(k * 2 + 1) * kST + tid];
+                    }
+
+                    // ---- D(cur) ------------------------------------------------------------------------
+                    if (d_grad || d_zero) {
+                        const int jk = c_j0 + k * kStep;
+                        float2 g[4];
+                        if (d_grad) {
+                            if (c_kl) tmem_ld_wait(wv);
+                            g[0] = __ffma2_rn(make_float2(e0.x, e0.y), A2, as_f2(wv[0], wv[1]));
+                            g[1] = __ffma2_rn(make_float2(e0.z, e0.w), A2, as_f2(wv[2], wv[3]));
+                            g[2] = __ffma2_rn(make_float2(e1.x, e1.y), A2, as_f2(wv[4], wv[5]));
+                            g[3] = __ffma2_rn(make_float2(e1.z, e1.w), A2, as_f2(wv[6], wv[7]));
+                            if (c_cet) {
+                                // CE on the raw logits of a tempered KL row: the row is read once more
+                                uint4 v[1];
+                                float2 x[4];
+                                load_row_vecs<DT, 1>(v, c_xr, jk, kStep, V, 16, lane);
+                                mask_row_vecs<DT, 1>(v, jk, kStep, V, lane);
+                                unpack2<DT>(v[0], x);
+                                const float2 l2 = splat(kLog2e), nm = splat(-mc_cur), cq2 = splat(cq);
+#pragma unroll
+                                for (int h = 0; h < 4; ++h) {
+                                    const float2 u = __ffma2_rn(x[h], l2, nm);
+                                    g[h] = __ffma2_rn(make_float2(ex2(u.x), ex2(u.y)), cq2, g[h]);
+                                }
+                            }
+                            if (c_ce) {
+                                const unsigned rel = (unsigned)(c_lab - jk);
+                                if (rel < (unsigned)EPV && c_lab >= 0) {
+#pragma unroll
+                                    for (int h = 0; h < 4; ++h) {
+                                        if ((int)rel == 2 * h) g[h].x -= ce_on;
+                                        if ((int)rel == 2 * h + 1) g[h].y -= ce_on;
+                                    }
+                                }
+                            }
+                        } else {
+                            g[0] = g[1] = g[2] = g[3] = splat(0.f);
+                        }
+                        const int jwk = jk - lane * EPV;                    // lane 0's element of vector k
+                        if (g_vec && jwk >= 0 && jwk + 32 * EPV <= V) {
+                            st_vec(reinterpret_cast<uint4*>(gp + (int64_t)jk * EB),
+                                   make_uint4(pack2<DT>(g[0]), pack2<DT>(g[1]), pack2<DT>(g[2]), pack2<DT>(g[3])));
+                        } else {
+                            const float gr[EPV] = {g[0].x, g[0].y, g[1].x, g[1].y, g[2].x, g[2].y, g[3].x, g[3].y};
+                            store_row_vec<DT>(gp, jk, V, g_vec, gr);
+                        }
+                    }
+
+                    // ---- B(nxt) ------------------------------------------------------------------------
+                    if (n_work) {
+                        const int jk = n_j0 + k * kStep;
+                        const int jwk = jk - lane * EPV;
+                        const bool inside = jwk >= 0 && jwk + 32 * EPV <= V;
+                        if (!inside) raw_s = mask_vec<DT>(raw_s, jk, V);
+                        float2 x[4];
+                        unpack2<DT>(raw_s, x);
+                        if (nx_kl) {
+                            if (n_d) raw_t = shift_granules(raw_t, raw_t2, n_d);
+                            if (!inside) raw_t = mask_vec<DT>(raw_t, jk, V);
+                        }
+                        if (release) {                                      // the slot may be refilled
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_a(bar_s);
+                        }
+                        if (n_cet) {
+                            const float2 l2 = splat(kLog2e), nm = splat(-nref_c);
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                const float2 u = __ffma2_rn(x[h], l2, nm);
+                                zc2 = __fadd2_rn(zc2, make_float2(ex2(u.x), ex2(u.y)));
+                            }
+                        }
+                        if (rnd_row) {   // the tempered logit is stored in the logits' dtype (icv_module.py:122-123)
+#pragma unroll
+                            for (int h = 0; h < 4; ++h)
+                                x[h] = make_float2(Fmt<DT>::round(x[h].x * it_row), Fmt<DT>::round(x[h].y * it_row));
+                        }
+                        {
+                            const float2 c2 = splat(c_row), nm = splat(-nref_s);
+                            float2 ev[4];
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                const float2 u = __ffma2_rn(x[h], c2, nm);
+                                ev[h] = make_float2(ex2(u.x), ex2(u.y));
+                                zs2 = __fadd2_rn(zs2, ev[h]);
+                            }
+                            cs[(k * 2) * kST + tid] = make_float4(ev[0].x, ev[0].y, ev[1].x, ev[1].y);
+                            cs[(k * 2 + 1) * kST + tid] = make_float4(ev[2].x, ev[2].y, ev[3].x, ev[3].y);
+                        }
+                        if (nx_kl) {
+                            unpack2<DT>(raw_t, x);
+                            if (rnd_row) {
+#pragma unroll
+                                for (int h = 0; h < 4; ++h)
+                                    x[h] = make_float2(Fmt<DT>::round(x[h].x * it_row), Fmt<DT>::round(x[h].y * it_row));
+                            }
+                            const float2 c2 = splat(c_row), nm = splat(-nref_t);
+                            float ev[8];
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                const float2 u = __ffma2_rn(x[h], c2, nm);
+                                const float2 e = make_float2(ex2(u.x), ex2(u.y));
+                                zt2 = __fadd2_rn(zt2, e);
+                                ev[2 * h] = e.x;
+                                ev[2 * h + 1] = e.y;
+                            }
+                            tmem_st8(tcol + k * 8, ev);
+                        }
+                    }
+                }
+            }
+            if (nx_kl) tmem_wait_st();
+            LICV_STAMP(4);
+#ifdef LICV_TRACE
+            if (it >= 2) ph_[6] += 1;
+#endif
+
+            // ---- cur is finished ----------------------------------------------------------------
+            if (c_valid && tid == 0) {
+                row_kl[c_r] = kl_row;
+                row_ce[c_r] = ce_row;
+            }
+            if (!n_valid) break;
+            // ---- nxt becomes cur ----------------------------------------------------------------
+            zs = zs2.x + zs2.y;
+            zt = zt2.x + zt2.y;
+            zc = zc2.x + zc2.y;
+            ref_s = nref_s;
+            ref_t = nref_t;
+            ref_c = nref_c;
+            c_flags = n_flags;
+            c_tr = n_tr;
+            c_lab = n_lab;
+            c_j0 = n_j0;
+            c_kfull = n_kfull;
+            c_xr = n_xr;
+            c_gp = reinterpret_cast<char*>(((uint64_t)nd1.w << 32) | nd1.z);
+            x_lab = __uint_as_float(nd2.x);
+            c_r = (int64_t)(((uint64_t)nd2.w << 32) | nd2.z);
+            ++it;
+            if ((it & (kDescRows - 1)) == 0) fill_desc(it);
+        }
+#ifdef LICV_TRACE
+        if ((blockIdx.x == 0 || blockIdx.x == 5) && lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g_sphase[((blockIdx.x ? 1 : 0) * 16 + warp) * 8 + i] = ph_[i];
+        }
+#endif
+    }
+
+    // TMEM is released by the warp that allocated it, after every warp is done with it
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+#ifdef LICV_TRACE
+    if (tid == 0 && blockIdx.x < 256) g_scta[blockIdx.x * 4 + 1] = globaltimer_ns();
+#endif
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(kCols)
+                     : "memory");
+    }
+    // ---- the last CTA to finish reduces the per-row losses (fixed order: deterministic) --------
+    if (tid == 0) {
+        __threadfence();
+        const unsigned done_ctas = atomicAdd(a.counter, 1u);
+        s_last = (done_ctas == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && tid < kST) {
+        __threadfence();
+        float* row_kl = a.row_loss;
+        float* row_ce = a.row_loss + a.n_rows;
+        float tk = 0.f, tc = 0.f;
+        for (int64_t i = tid; i < a.n_rows; i += kST) {
+            tk += __ldcg(row_kl + i);
+            tc += __ldcg(row_ce + i);
+        }
+        tk = warp_sum(tk);
+        tc = warp_sum(tc);
+        if (lane == 0) { s_tot[warp] = tk; s_tot[kSW + warp] = tc; }
+        compute_sync();
+        if (tid == 0) {
+            tk = 0.f; tc = 0.f;
+            for (int w = 0; w < kSW; ++w) { tk += s_tot[w]; tc += s_tot[kSW + w]; }
+            const float kl = use_kl ? tk * T * T / (float)n_kl : 0.f;
+            const float ce = use_ce ? tc / (float)n_ce : 0.f;
+            a.out_losses[0] = kl;
+            a.out_losses[1] = ce;
+            a.out_losses[2] = a.only_hard_loss ? ce : (use_ce ? fmaf(a.hard_loss_weight, ce, kl) : kl);
+            *a.counter = 0u;
+        }
+    }
+}
+
+inline int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
+}
+
+template <int DT, int NV>
+int launch_stream(const KdArgs& a, cudaStream_t st) {
+    auto kern = kd_loss_stream_kernel<DT, NV>;
+    constexpr size_t smem = (size_t)NV * 2 * kST * 16 + (size_t)stream_slots(NV) * kSlotBytes;
+    // the attribute is per device and per function: set it on every launch (a host-side store)
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int64_t grid = a.n_rows < device_info().sm_count ? a.n_rows : device_info().sm_count;
+    if (grid < 1) grid = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kBlock);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    cfg.attrs = attr;
+    cfg.numAttrs = launch_attrs(attr, 0);
+    return (int)cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+}  // namespace
+
+#ifdef LICV_TRACE
+extern "C" int licv_debug_read_stream_trace(unsigned long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g_scta, sizeof(unsigned long long) * n);
+}
+extern "C" int licv_debug_read_stream_phases(long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g_sphase, sizeof(long long) * n);
+}
+#endif
+
+static int g_stream_on = -1;
+// debug / A-B timing: 1 = stream kernel, 0 = the round-1 kernels, -1 = LICV_KD_STREAM (default 1)
+extern "C" void licv_debug_set_kd_stream(int on) { g_stream_on = on; }
+
+bool kd_stream_plan(int vocab, int dtype) {
+    static const int env_on = env_int("LICV_KD_STREAM", 1);   // 0: the round-1 kernels
+    const int on = g_stream_on >= 0 ? g_stream_on : env_on;
+    if (!on || dtype == LICV_F32) return false;
+    const int64_t nvec = ((int64_t)vocab + 7) / 8 + 1;    // + 1: a row may straddle a granule
+    return nvec > 4 * kST && nvec <= 8 * kST;             // 16 377 .. 32 760 elements
+}
+int launch_kd_stream(const KdArgs& a, int dtype, cudaStream_t st) {
+    return dtype == LICV_BF16 ? launch_stream<LICV_BF16, 8>(a, st) : launch_stream<LICV_F16, 8>(a, st);
+}
+
+}  // namespace licv

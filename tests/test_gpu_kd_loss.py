@@ -67,6 +67,12 @@ CASES = [  # R, Rt, V, dtype, T, lambda
     (6, 6, 8, "fp32", 0.5, 1.0),
     (5, 9, 257, "fp16", 2.0, 0.5),
     (40, 64, 50257, "bf16", 1.0, 0.5),
+    # KL + CE rows at T != 1 on the 32k vocabularies (decay_temperature makes T != 1 a live state,
+    # icv_module.py:150-158): the CE term works on the raw logits next to the tempered KL
+    (12, 30, 32002, "bf16", 2.0, 0.5),
+    (12, 30, 32002, "fp16", 0.5, 0.5),
+    (7, 9, 32003, "bf16", 1.5, 0.25),
+    (6, 11, 20011, "bf16", 1.0, 0.5),
 ]
 
 
@@ -236,3 +242,74 @@ def test_kd_loss_full_size_properties(ops):
     got = host(dstu[idx]) * (R / len(idx))
     assert rel_err(got, want["d_stu"]) < 1.2 * EPS["bf16"]
     assert np.isfinite(float(losses[2]))
+
+
+def test_kd_loss_far_from_first_vector_and_minus_inf(ops):
+    """Rows whose large logits sit far (in octaves) above what a thread sees first: the stream
+    kernel takes its exponentials relative to the thread's first vector and must rebuild such a
+    row with exact maxima; -inf logits (masked vocabulary entries) are legal inputs."""
+    rng = np.random.default_rng(21)
+    for dt, V in [("bf16", 32002), ("fp16", 32003)]:
+        R = 6
+        stu_np = rng.normal(size=(R, V)) * 3
+        tea_np = rng.normal(size=(R, V)) * 3
+        stu_np[0, :4300] -= 200.0            # every thread's first vector is 288 octaves down
+        tea_np[1, :4300] -= 150.0
+        stu_np[2, :4300] = -np.inf           # first vectors hold nothing finite
+        tea_np[2, 100:5000] = -np.inf
+        stu_np[3, 7::13] = -np.inf           # scattered masked entries (the regular path)
+        tea_np[4, 20000] += 120.0            # one teacher logit 170 octaves above the rest
+        stu_np[4, 20000] += 60.0
+        stu = dev(stu_np, TD[dt])
+        tea = dev(tea_np, TD[dt])
+        ktr = np.arange(R, dtype=np.int32)
+        lab = rng.integers(5000, V, size=R).astype(np.int64)
+        lab[3] = 5008                        # not one of row 3's masked entries
+        want = O.kd_loss_rows(host(stu), host(tea), ktr, lab, 1.0, 1e-6, 0.5)
+        assert np.isfinite(want["loss"])
+        for in_place in (False, True):
+            losses, dstu = ops.kd_loss_raw(stu.clone(), tea, torch.tensor(ktr).cuda(),
+                                           torch.tensor(lab).cuda(), None, want["N"], want["M"],
+                                           1.0, 1e-6, 0.5, in_place=in_place)
+            assert abs(float(losses[0]) - want["kl"]) <= 1e-5 * abs(want["kl"]) + 1e-7
+            assert abs(float(losses[1]) - want["ce"]) <= 1e-5 * abs(want["ce"]) + 1e-7
+            assert rel_err(host(dstu), want["d_stu"]) < 1.2 * EPS[dt]
+
+
+def test_kd_loss_config1_training_shape_in_place(ops):
+    """BASELINE configs[1] (idefics-9B, VQAv2 32-shot, bs 8, fp16-mixed): 256 student rows of
+    32002 fp16 logits, 32 KL rows paired with a compact teacher [32, V], 248 CE rows,
+    hard_loss_weight 0.5, gradient written in place."""
+    rng = np.random.default_rng(426)
+    B, Tq, V = 8, 32, 32002
+    R = B * Tq
+    stu_np = rng.normal(size=(R, V)) * 3
+    tea_np = rng.normal(size=(32, V)) * 3
+    ktr = np.full(R, -1, np.int32)
+    lab = rng.integers(3, V, size=R).astype(np.int64)
+    n = 0
+    for b in range(B):
+        lab[b * Tq + Tq - 1] = -100                     # the shifted CE has no target for the last token
+        for t in range(Tq - 5, Tq - 1):                 # 4 answer tokens per sample
+            ktr[b * Tq + t] = n
+            j = rng.integers(0, V)
+            tea_np[n, j] += 10
+            if n % 2:
+                stu_np[b * Tq + t, j] += 8
+            n += 1
+    stu = dev(stu_np, torch.float16)
+    tea = dev(tea_np, torch.float16)
+    want = O.kd_loss_rows(host(stu), host(tea), ktr, lab, 1.0, 1e-6, 0.5, logit_fmt="fp16")
+    assert (want["N"], want["M"]) == (32, 248)
+    counts = torch.tensor([32, 248, 32, 0], dtype=torch.int32).cuda()
+    losses, dstu = ops.kd_loss_raw(stu, tea, torch.tensor(ktr).cuda(), torch.tensor(lab).cuda(),
+                                   counts, temperature=1.0, kl_eps=1e-6, hard_loss_weight=0.5,
+                                   in_place=True)
+    assert dstu.data_ptr() == stu.data_ptr()
+    kl, ce, tot = [float(x) for x in losses]
+    assert abs(kl - want["kl"]) <= 1e-5 * abs(want["kl"]) + 1e-7
+    assert abs(ce - want["ce"]) <= 1e-5 * abs(want["ce"]) + 1e-7
+    assert abs(tot - want["loss"]) <= 1e-5 * abs(want["loss"]) + 1e-7
+    assert rel_err(host(dstu), want["d_stu"]) < 1.2 * EPS["fp16"]
+    dead = (ktr < 0) & (lab == -100)
+    assert not host(dstu)[dead].any()

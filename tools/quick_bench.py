@@ -21,7 +21,53 @@ except Exception:
     pass
 
 
-def time_graph(launch, nbuf, reps=5):
+class Clocks:
+    """SM clock / power samples (NVML) while a timed region runs."""
+
+    def __init__(self):
+        import threading
+        self.mhz, self.watts, self._stop = [], [], threading.Event()
+        self.mem_mhz, self.reasons, self.temps = [], 0, []
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device())
+        except Exception:
+            self.nv = None
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set() and self.nv is not None:
+            try:
+                self.mhz.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.watts.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                self.mem_mhz.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_MEM))
+                self.reasons |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.temps.append(self.nv.nvmlDeviceGetTemperature(self.h, self.nv.NVML_TEMPERATURE_GPU))
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join()
+
+    def summary(self):
+        m = sorted(self.mhz)
+        return {"sm_mhz": m[len(m) // 2] if m else None, "sm_mhz_min": m[0] if m else None,
+                "watts_max": round(max(self.watts), 1) if self.watts else None,
+                "mem_mhz_min": min(self.mem_mhz) if self.mem_mhz else None,
+                "reasons": hex(self.reasons), "temp_max": max(self.temps) if self.temps else None}
+
+
+LAST_CLOCKS = {}
+
+
+def time_graph(launch, nbuf, reps=5, min_seconds=0.25):
     """launch(k) enqueues one kernel on buffer set k; returns seconds per launch."""
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
@@ -42,7 +88,34 @@ def time_graph(launch, nbuf, reps=5):
             g.replay()
         e1.record(s)
         s.synchronize()
-    return e0.elapsed_time(e1) * 1e-3 / (reps * nbuf)
+        t = e0.elapsed_time(e1) * 1e-3 / (reps * nbuf)
+        # a second, longer region with the clocks sampled: what the SM clock settles to under load
+        n2 = max(reps, int(min_seconds / max(t * nbuf, 1e-6)))
+        with Clocks() as ck:
+            e0.record(s)
+            for _ in range(n2):
+                g.replay()
+            e1.record(s)
+            s.synchronize()
+        LAST_CLOCKS.clear()
+        LAST_CLOCKS.update(ck.summary(), us_sustained=round(e0.elapsed_time(e1) * 1e3 / (n2 * nbuf), 2))
+    return t
+
+
+def cta_stats(lib):
+    """Debug builds (-DLICV_TRACE): duration of every CTA of the last stream-kernel launch."""
+    if not hasattr(lib, "licv_debug_read_stream_trace"):
+        return {}
+    import ctypes
+    import numpy as np
+    buf = (ctypes.c_ulonglong * (256 * 4))()
+    lib.licv_debug_read_stream_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.licv_debug_read_stream_trace(buf, 256 * 4)
+    t = np.array(buf, dtype=np.int64).reshape(256, 4)[:148]
+    dur = (t[:, 1] - t[:, 0]) / 1e3
+    return {"cta_us_min": round(float(dur.min()), 1), "cta_us_med": round(float(np.median(dur)), 1),
+            "cta_us_max": round(float(dur.max()), 1),
+            "cta_start_spread_us": round(float((t[:, 0].max() - t[:, 0].min()) / 1e3), 1)}
 
 
 def main():
@@ -62,6 +135,7 @@ def main():
     d = args.d
     if "inject" in args.which:
         for n_tok in [int(x) for x in args.tokens.split(",")]:
+            torch.cuda.empty_cache()
             nbuf = max(2, min(32, int(600e6 // (n_tok * d * e * 3)) + 1))
             hs = [(torch.randn(n_tok, d, device="cuda") * 4).to(dt) for _ in range(nbuf)]
             gs = [torch.randn(n_tok, d, device="cuda").to(dt) for _ in range(nbuf)]
@@ -85,11 +159,15 @@ def main():
                 gbs = nb * n_tok * d / t / 1e9
                 print(json.dumps(dict(kernel=name, n_tok=n_tok, d=d, dtype=args.dtype,
                                       us=round(t * 1e6, 2), gbs=round(gbs, 1),
-                                      frac=round(gbs / PEAK, 4))), flush=True)
+                                      frac=round(gbs / PEAK, 4), **LAST_CLOCKS)), flush=True)
             del hs, gs, outs
     if "kd" in args.which:
         V = args.vocab
         for R in [int(x) for x in args.rows.split(",")]:
+            # fresh segments for every size: buffers carved out of blocks that the caching allocator
+            # kept from a smaller size have shown 2-4x lower bandwidth for every kernel, torch's own
+            # copy included (profiles/README.md, r2q)
+            torch.cuda.empty_cache()
             nbuf = max(2, min(8, int(600e6 // (R * V * e * 3)) + 1))
             stus = [(torch.randn(R, V, device="cuda") * 3).to(dt) for _ in range(nbuf)]
             teas = [(torch.randn(R, V, device="cuda") * 3).to(dt) for _ in range(nbuf)]
@@ -117,7 +195,8 @@ def main():
                 gbs = nb * R * V / t / 1e9
                 print(json.dumps(dict(kernel=name, R=R, V=V, dtype=args.dtype,
                                       us=round(t * 1e6, 2), gbs=round(gbs, 1),
-                                      frac=round(gbs / PEAK, 4))), flush=True)
+                                      frac=round(gbs / PEAK, 4), **LAST_CLOCKS, **cta_stats(lib))),
+                      flush=True)
             del stus, teas, dst
 
 

@@ -170,6 +170,18 @@ int licv_kd_select_rows(const int64_t* stu_ids, const int64_t* stu_mask_length,
  *   allocation; they never enter the result).
  * ------------------------------------------------------------------------------------------ */
 int64_t licv_kd_loss_workspace_bytes(int64_t n_rows);
+/* Which kernel licv_kd_loss_fwd_bwd runs for a vocabulary / dtype / temperature / row count
+ * (kl_and_ce != 0: rows carry both a KL and a CE term).  A pure function of its arguments, the
+ * device's SM count and the environment
+ * switches LICV_KD_STREAM / LICV_KD_TMEM / LICV_KD_NO_CLUSTER; negative = LICV_ERR_*. */
+#define LICV_KD_KERNEL_GENERIC 0 /* one CTA per row, sweeps re-read the row from L2 */
+#define LICV_KD_KERNEL_CLUSTER 1 /* row pair cached across a thread-block cluster */
+#define LICV_KD_KERNEL_TMEM 2    /* row pair cached in shared + tensor memory, one CTA per SM */
+#define LICV_KD_KERNEL_STREAM 3  /* TMA-staged rows, gradient sweep fused with the next row's exponentials */
+int licv_kd_loss_plan(int vocab, int dtype, float temperature, int kl_and_ce, int64_t n_rows);
+/* Test / timing hook: 0 = never the stream kernel, 1 = where it is the faster one (default),
+ * 2 = wherever it can run, -1 = back to the environment (LICV_KD_STREAM).  Process-wide. */
+void licv_debug_set_kd_stream(int mode);
 int licv_kd_loss_fwd_bwd(const void* stu, void* dstu, const void* tea, const int32_t* kl_tea_row,
                          const int64_t* ce_label, const int32_t* counts, int64_t n_kl, int64_t n_ce,
                          float temperature, float kl_eps, float hard_loss_weight,

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("LICV_LIB") or os.path.join(_PKG, "lib", "liblicv_b200
 
 F32, BF16, F16 = 0, 1, 2
 ROUND_Y, ROUND_NH, ROUND_NY, ROUND_T, ROUND_TEMPERED = 1, 2, 4, 8, 16
+KD_KERNEL_GENERIC, KD_KERNEL_CLUSTER, KD_KERNEL_TMEM, KD_KERNEL_STREAM = 0, 1, 2, 3
 
 _lib = None
 _lock = threading.Lock()
@@ -36,6 +37,8 @@ SIGNATURES = {
     "licv_kd_select_rows": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32,
                                    _vp, _vp, _vp, _vp, _vp]),
     "licv_kd_loss_workspace_bytes": (_i64, [_i64]),
+    "licv_kd_loss_plan": (_i32, [_i32, _i32, _f32, _i32, _i64]),
+    "licv_debug_set_kd_stream": (None, [_i32]),
     "licv_kd_loss_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32,
                                     _i32, _f32, _vp, _vp, _i64, _i32, _i64, _i64, _i32, _u32, _vp]),
     "licv_scale_inplace": (_i32, [_vp, _i64, _vp, _i32, _vp]),

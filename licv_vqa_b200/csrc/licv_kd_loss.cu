@@ -338,6 +338,29 @@ int launch_kd_generic(const KdArgs& a, int dtype, cudaStream_t st) {
 
 using namespace licv;
 
+namespace {
+// The stream kernel needs a few rows per CTA to reach its steady state (its first row pays for the
+// TMA ring fill and a CTA-wide look at the first chunk): measured against the tensor-memory
+// kernel, 32 002 bf16 logits, it wins from ~256 KL+CE rows / ~1000 CE-only rows on (profiles/
+// r2_kd_small_rows.txt).  Below 4 rows per SM the tensor-memory kernel runs where it can.
+int kd_pick(int vocab, int dtype, float temperature, bool kl_and_ce, int64_t n_rows, int* C, int* NV, int* NT) {
+    const bool tmem_ok = kd_tmem_plan(vocab, dtype, temperature, kl_and_ce);
+    const int sms = device_info().status == LICV_OK ? device_info().sm_count : 148;
+    if (kd_stream_plan(vocab, dtype) && (!tmem_ok || n_rows >= (int64_t)4 * sms || kd_stream_forced()))
+        return LICV_KD_KERNEL_STREAM;
+    if (tmem_ok) return LICV_KD_KERNEL_TMEM;
+    if (kd_cluster_plan(vocab, dtype, temperature, kl_and_ce, C, NV, NT)) return LICV_KD_KERNEL_CLUSTER;
+    return LICV_KD_KERNEL_GENERIC;
+}
+}  // namespace
+
+extern "C" int licv_kd_loss_plan(int vocab, int dtype, float temperature, int kl_and_ce, int64_t n_rows) {
+    if (dtype != LICV_F32 && dtype != LICV_BF16 && dtype != LICV_F16) return LICV_ERR_BAD_DTYPE;
+    if (vocab <= 0 || n_rows < 0) return LICV_ERR_BAD_ARGUMENT;
+    int C = 0, NV = 0, NT = 0;
+    return kd_pick(vocab, dtype, temperature, kl_and_ce != 0, n_rows, &C, &NV, &NT);
+}
+
 extern "C" int64_t licv_kd_loss_workspace_bytes(int64_t n_rows) {
     if (n_rows < 0) n_rows = 0;
     return 16 + ((2 * n_rows * (int64_t)sizeof(float) + 15) / 16) * 16;
@@ -377,14 +400,13 @@ extern "C" int licv_kd_loss_fwd_bwd(const void* stu, void* dstu, const void* tea
     a.n_rows = n_rows; a.vocab = vocab; a.stu_stride = stu_stride; a.tea_stride = tea_stride;
     a.round_flags = round_flags;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (kd_stream_plan(vocab, dtype)) return launch_kd_stream(a, dtype, st);
-    if (kd_tmem_plan(vocab, dtype, temperature, ce_label != nullptr && !only_hard_loss))
-        return launch_kd_tmem(a, dtype, st);
     int C = 0, NV = 0, NT = 0;
-    if (kd_cluster_plan(vocab, dtype, temperature, ce_label != nullptr && !only_hard_loss, &C, &NV,
-                        &NT))
-        return launch_kd_cluster(a, dtype, C, NV, NT, st);
-    return launch_kd_generic(a, dtype, st);
+    switch (kd_pick(vocab, dtype, temperature, ce_label != nullptr && !only_hard_loss, n_rows, &C, &NV, &NT)) {
+        case LICV_KD_KERNEL_STREAM: return launch_kd_stream(a, dtype, st);
+        case LICV_KD_KERNEL_TMEM: return launch_kd_tmem(a, dtype, st);
+        case LICV_KD_KERNEL_CLUSTER: return launch_kd_cluster(a, dtype, C, NV, NT, st);
+        default: return launch_kd_generic(a, dtype, st);
+    }
 }
 
 extern "C" int licv_scale_inplace(void* x, int64_t n, const float* scale, int dtype,

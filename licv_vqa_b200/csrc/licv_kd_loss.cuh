@@ -36,6 +36,7 @@ int launch_kd_tmem(const KdArgs& a, int dtype, cudaStream_t st);
 // stream kernel (licv_kd_loss_stream.cu): 16-bit logits, 16 377 <= V <= 32 752; TMA-staged rows,
 // sweep D of a row fused with sweep B of the next (LICV_KD_STREAM=0 disables it)
 bool kd_stream_plan(int vocab, int dtype);
+bool kd_stream_forced();   // LICV_KD_STREAM=2 / licv_debug_set_kd_stream(2): also for a handful of rows
 int launch_kd_stream(const KdArgs& a, int dtype, cudaStream_t st);
 int launch_kd_cluster(const KdArgs& a, int dtype, int C, int NV, int NT, cudaStream_t st);
 

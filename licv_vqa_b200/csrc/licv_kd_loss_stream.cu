@@ -844,13 +844,7 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
 #pragma unroll 1
                 for (int k = 0; k < NV; k += 2) {
                     step(k, ra, rb);
-#ifdef LICV_KD_LOCKSTEP
-                    asm volatile("bar.sync %0, 128;" ::"r"(2 + (warp & 3)) : "memory");
-#endif
                     step(k + 1, rb, ra);
-#ifdef LICV_KD_LOCKSTEP
-                    asm volatile("bar.sync %0, 128;" ::"r"(2 + (warp & 3)) : "memory");
-#endif
                 }
             };
             LICV_STAMP(3);
@@ -1118,17 +1112,21 @@ extern "C" int licv_debug_read_stream_phases(long long* host, int n) {
 }
 #endif
 
-static int g_stream_on = -1;
-// debug / A-B timing: 1 = stream kernel, 0 = the round-1 kernels, -1 = LICV_KD_STREAM (default 1)
-extern "C" void licv_debug_set_kd_stream(int on) { g_stream_on = on; }
+static int g_stream_mode = -1;
+// 0 = never, 1 = where it is the faster kernel (default), 2 = wherever it can run; -1 = from the
+// environment (LICV_KD_STREAM, default 1).  Tests pin 0 and 2 to cover both families of kernels.
+extern "C" void licv_debug_set_kd_stream(int mode) { g_stream_mode = mode; }
+static int stream_mode() {
+    static const int env_mode = env_int("LICV_KD_STREAM", 1);
+    return g_stream_mode >= 0 ? g_stream_mode : env_mode;
+}
 
 bool kd_stream_plan(int vocab, int dtype) {
-    static const int env_on = env_int("LICV_KD_STREAM", 1);   // 0: the round-1 kernels
-    const int on = g_stream_on >= 0 ? g_stream_on : env_on;
-    if (!on || dtype == LICV_F32) return false;
+    if (stream_mode() == 0 || dtype == LICV_F32) return false;
     const int64_t nvec = ((int64_t)vocab + 7) / 8 + 1;    // + 1: a row may straddle a granule
     return nvec > 4 * kST && nvec <= 8 * kST;             // 16 377 .. 32 760 elements
 }
+bool kd_stream_forced() { return stream_mode() == 2; }
 int launch_kd_stream(const KdArgs& a, int dtype, cudaStream_t st) {
     return dtype == LICV_BF16 ? launch_stream<LICV_BF16, 8>(a, st) : launch_stream<LICV_F16, 8>(a, st);
 }

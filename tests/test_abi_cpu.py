@@ -237,3 +237,25 @@ def test_collator_contract_from_token_ids():
         check_batch_contract({"inputs": batch["inputs"]}, PAD)
     left = collate_token_ids(query, query_x, ice, PAD, BOS, EOS, padding_side="left")
     assert left["query_inputs"]["input_ids"][1].tolist() == [0, 0, 1, 21, 22, 95, 2]
+
+
+def test_kd_loss_plan_fast_kernel_for_reference_vocabularies():
+    """Every reference model's vocabulary (idefics-9b 32002, idefics2-8b 32003, config 1's 32000)
+    runs on the stream kernel for 16-bit logits - also KL + CE rows at T != 1 (decay_temperature,
+    icv_module.py:150-158), which round 1 left to the generic kernel."""
+    from licv_vqa_b200 import _abi
+    lib = _abi.load()
+    for V in (32000, 32002, 32003):
+        for code in (_abi.BF16, _abi.F16):
+            for T in (1.0, 0.5, 2.0):
+                assert lib.licv_kd_loss_plan(V, code, T, 1, 8192) == _abi.KD_KERNEL_STREAM
+            # a handful of rows per SM: the tensor-memory kernel where it can (T = 1 or one loss)
+            assert lib.licv_kd_loss_plan(V, code, 1.0, 1, 256) == _abi.KD_KERNEL_TMEM
+            assert lib.licv_kd_loss_plan(V, code, 2.0, 0, 256) == _abi.KD_KERNEL_TMEM
+            assert lib.licv_kd_loss_plan(V, code, 2.0, 1, 256) == _abi.KD_KERNEL_STREAM
+        assert lib.licv_kd_loss_plan(V, _abi.F32, 1.0, 1, 8192) == _abi.KD_KERNEL_CLUSTER
+    assert lib.licv_kd_loss_plan(1003, _abi.BF16, 1.0, 1, 8192) == _abi.KD_KERNEL_TMEM
+    assert lib.licv_kd_loss_plan(50257, _abi.BF16, 1.0, 1, 8192) == _abi.KD_KERNEL_CLUSTER
+    assert lib.licv_kd_loss_plan(50257, _abi.BF16, 2.0, 1, 8192) == _abi.KD_KERNEL_GENERIC
+    assert lib.licv_kd_loss_plan(300000, _abi.BF16, 1.0, 0, 8192) == _abi.KD_KERNEL_GENERIC
+    assert lib.licv_kd_loss_plan(0, _abi.BF16, 1.0, 0, 8192) < 0

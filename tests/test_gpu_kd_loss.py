@@ -14,10 +14,16 @@ pytestmark = pytest.mark.gpu
 TD = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
 
 
-@pytest.fixture(scope="module")
-def ops():
-    from licv_vqa_b200 import ops as _ops
-    return _ops
+@pytest.fixture(scope="module", params=["auto", "stream", "round1"])
+def ops(request):
+    """The whole file runs three times: the dispatcher's own choice, the stream kernel wherever it
+    can run (the small row counts of these tests would otherwise go to the tensor-memory kernel),
+    and the round-1 kernels only."""
+    from licv_vqa_b200 import _abi, ops as _ops
+    lib = _abi.load()
+    lib.licv_debug_set_kd_stream({"auto": 1, "stream": 2, "round1": 0}[request.param])
+    yield _ops
+    lib.licv_debug_set_kd_stream(-1)
 
 
 def dev(a, dtype):
@@ -313,3 +319,4 @@ def test_kd_loss_config1_training_shape_in_place(ops):
     assert rel_err(host(dstu), want["d_stu"]) < 1.2 * EPS["fp16"]
     dead = (ktr < 0) & (lab == -100)
     assert not host(dstu)[dead].any()
+

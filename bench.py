@@ -12,8 +12,8 @@ non-pad position a CE row, hard_loss_weight = 0.5), on synthetic tensors:
     icv = sigmoid?(alpha) * v                                  licv_icv_scale
     32 x  out_l = inject(h_l, icv_l)                           licv_inject_fwd
     row pairing + labels, KL + 0.5 CE fwd+bwd on the logits     licv_kd_prepare_rows, licv_kd_loss_fwd_bwd
-    32 x  dh_l, d_icv_l += inject_bwd(h_l, g_l, icv_l)          licv_inject_bwd
-    d_v, d_alpha                                                licv_icv_scale_bwd
+    32 x  dh_l, replicas_l += inject_bwd(h_l, g_l, icv_l)       licv_inject_bwd_spread
+    d_icv = sum of the replicas; d_v, d_alpha                   licv_reduce_rows, licv_icv_scale_bwd
     (N > 1) all-reduce of the flat ICV gradient (131 104 fp32)  NCCL
     clip + AdamW on the flat ICV parameters                     licv_adamw_step
 
@@ -190,6 +190,9 @@ class HotPath:
         self.ws = torch.zeros(self.lib.licv_kd_loss_workspace_bytes(B * T) + 64, dtype=torch.uint8,
                               device=device)
         self.opt_ws = torch.zeros(16, dtype=torch.uint8, device=device)
+        # the backward launches add their d_shift into replicas of the [L, d] gradient (zero between steps)
+        self.n_rows = self.lib.licv_inject_bwd_rows(B * T, d, self.code, self.code)
+        self.rows = torch.zeros(L, self.n_rows, d, **f32)
         self.out = [torch.empty(B * T, d, dtype=dtype, device=device) for _ in range(L)]
         self.dh = [torch.empty(B * T, d, dtype=dtype, device=device) for _ in range(L)]
         self.dstu = torch.empty(B * T, V, dtype=dtype, device=device)
@@ -240,12 +243,15 @@ class HotPath:
             CFG["temperature"], CFG["kl_eps"], CFG["hard_loss_weight"], 0, 1.0,
             self.losses.data_ptr(), self.ws.data_ptr(), n_tok, V, V, V, self.code,
             self.abi.ROUND_TEMPERED, st), "kd_loss")
-        self.sink.zero_()
+        R = self.n_rows
         for l in reversed(range(L)):
-            self._chk(lib.licv_inject_bwd(batch["h"][l].data_ptr(), batch["g"][l].data_ptr(),
-                                          self.icv[l].data_ptr(), self.dh[l].data_ptr(),
-                                          self.sink[l].data_ptr(), n_tok, d, self.code, self.code,
-                                          self.flags, st), "inject_bwd")
+            self._chk(lib.licv_inject_bwd_spread(
+                batch["h"][l].data_ptr(), batch["g"][l].data_ptr(), self.icv[l].data_ptr(),
+                self.dh[l].data_ptr(), self.rows[l].data_ptr(), R, n_tok, d, self.code, self.code,
+                self.flags, st), "inject_bwd_spread")
+        # d_icv = sum of the replicas (which the launch leaves zero for the next step)
+        self._chk(lib.licv_reduce_rows(self.rows.data_ptr(), self.sink.data_ptr(), L, R, R * d, d, 0, 1,
+                                       st), "reduce_rows")
         g = self.grad.data_ptr()
         self._chk(lib.licv_icv_scale_bwd(alpha_p, vec_p, self.sink.data_ptr(), g,
                                          g + 4 * self.n_vec, L, d, int(CFG["use_sigmoid"]), st),
@@ -608,13 +614,11 @@ def main():
         n_tok = CFG["batch_per_gpu"] * CFG["student_tokens"]
         es = esize(dtype)
         st = stream.cuda_stream
-        hp.sink.zero_()
-
         def bwd_launch(l):
-            return lambda: hp.lib.licv_inject_bwd(batch["h"][l].data_ptr(), batch["g"][l].data_ptr(),
-                                                  hp.icv[l].data_ptr(), hp.dh[l].data_ptr(),
-                                                  hp.sink[l].data_ptr(), n_tok, d, hp.code, hp.code,
-                                                  hp.flags, st)
+            return lambda: hp.lib.licv_inject_bwd_spread(
+                batch["h"][l].data_ptr(), batch["g"][l].data_ptr(), hp.icv[l].data_ptr(),
+                hp.dh[l].data_ptr(), hp.rows[l].data_ptr(), hp.n_rows, n_tok, d, hp.code, hp.code,
+                hp.flags, st)
 
         def fwd_launch(l):
             return lambda: hp.lib.licv_inject_fwd(batch["h"][l].data_ptr(), hp.icv[l].data_ptr(),

@@ -99,6 +99,27 @@ int licv_inject_bwd(const void* h, const void* g, const float* shift, void* dh, 
                     int64_t n_tokens, int d, int h_dtype, int g_dtype, unsigned round_flags,
                     licv_stream_t stream);
 
+/* a4, spread form: the same backward, but d_shift is ADDED (+=, fp32 atomics) into one of n_rows
+ * replicas of the [d] vector - CTA b of the launch takes replica b mod n_rows of `rows`
+ * [n_rows, d] - and the replicas of all layers are added up by ONE licv_reduce_rows launch at the
+ * end of the backward pass.  The L2 atomic units serialise per address: with one [d] vector per
+ * layer the 256 CTAs of a training-shape launch queue for 3.5 us (licv_inject_bwd pre-reduces
+ * across thread-block clusters instead, at the price of two cluster barriers); with <= 16 CTAs
+ * per replica the atomics are free.  `rows` must be zero before the first launch of a pass
+ * (licv_reduce_rows(..., clear = 1) leaves it so); n_rows is a power of two <= 64.
+ * licv_inject_bwd_rows: the replica count recommended for a launch of this shape (a pure
+ * function of its arguments and the device; 1 for rows the TMA kernel does not take);
+ * negative = LICV_ERR_*. */
+int licv_inject_bwd_rows(int64_t n_tokens, int d, int h_dtype, int g_dtype);
+int licv_inject_bwd_spread(const void* h, const void* g, const float* shift, void* dh, float* rows,
+                           int n_rows, int64_t n_tokens, int d, int h_dtype, int g_dtype,
+                           unsigned round_flags, licv_stream_t stream);
+/* out [n_layers, d] (+)= sum_p rows[l * layer_stride + p * d + c], p < n_rows  (fp32; layer_stride
+ * in floats, a multiple of 4, >= n_rows * d).  accumulate != 0 adds to `out` (gradient
+ * accumulation over micro-batches), 0 overwrites it; clear != 0 zero-fills the rows read. */
+int licv_reduce_rows(float* rows, float* out, int n_layers, int n_rows, int64_t layer_stride, int d,
+                     int accumulate, int clear, licv_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * a6  VQAICVModule.get_mask (icv_src/icv_module.py:136-148)
  *   mask[b,t] = (t >= mask_length[b]) && (input_ids[b,t] != pad_token_id), uint8 0/1 (torch.bool)

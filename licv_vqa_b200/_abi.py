@@ -31,6 +31,9 @@ SIGNATURES = {
     "licv_icv_scale_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "licv_inject_fwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _u32, _vp]),
     "licv_inject_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _u32, _vp]),
+    "licv_inject_bwd_rows": (_i32, [_i64, _i32, _i32, _i32]),
+    "licv_inject_bwd_spread": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _u32, _vp]),
+    "licv_reduce_rows": (_i32, [_vp, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _vp]),
     "licv_get_mask": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "licv_kd_prepare_rows": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32,
                                     _vp, _vp, _vp, _vp]),

@@ -148,7 +148,9 @@ struct Args {
     const uint4* g;       // backward only
     const float* shift;
     uint4* out;           // forward: out; backward: dh (may be null)
-    float* d_shift;       // backward only
+    float* d_shift;       // backward only: [d], accumulated (atomics)
+    float* rows;          // backward only: if set, CTA b adds its d_shift into rows[b & row_mask][d]
+    int row_mask;         //   (n_rows - 1, n_rows a power of two): fewer CTAs per atomic address
     int64_t n_tok;
     int nvec;             // 16-byte vectors per row of h
     int gt;               // threads per row group

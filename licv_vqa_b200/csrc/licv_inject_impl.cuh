@@ -13,7 +13,34 @@ struct Launch {
     RowPlan plan;
     unsigned flags;
     cudaStream_t stream;
+    int partial_rows = 0;   // > 0: backward in spread mode on exactly this many CTAs
 };
+
+// Spread backward: CTAs of a launch and the replica count that keeps <= 16 CTAs on one atomic
+// address.  Token batches as in dispatch_bwd_pipe_tb: one token per CTA until the machine is full
+// (tokens inside a CTA are processed one after the other, ~0.9 us each: at 256 tokens 256 CTAs x 1
+// token take 4.7 us, 128 x 2 5.0 us, 64 x 4 7.0 us, the cluster reduction 5.6 us), at most two CTAs
+// per SM.
+inline int pipe_partial_tb(int64_t n_tok, int nvec, int h_bytes, int g_bytes) {
+    const int vpt = nvec / kPipeThreads;
+    const int gv = g_bytes > h_bytes ? 2 : 1;
+    const int fit = 8 / (vpt * (1 + gv));
+    const int tb_big = fit >= 4 ? 4 : (fit >= 2 ? 2 : 1);
+    const int64_t fill = (int64_t)device_info().sm_count * 2;
+    return (tb_big > 1 && n_tok >= fill * tb_big) ? tb_big : 1;
+}
+inline int pipe_partial_ctas(int64_t n_tok, int nvec, int h_bytes, int g_bytes) {
+    const int tb = pipe_partial_tb(n_tok, nvec, h_bytes, g_bytes);
+    int64_t ctas = (n_tok + tb - 1) / tb;
+    const int64_t cap = (int64_t)device_info().sm_count * 2;
+    if (ctas > cap) ctas = cap;
+    return ctas < 1 ? 1 : (int)ctas;
+}
+inline int spread_rows_for(int ctas) {
+    int r = 1;
+    while (r < 16 && r * 16 < ctas) r *= 2;
+    return r;
+}
 
 template <int HDT, int ODT, int VPT, int TB, int RND>
 int launch_fwd(const Args& a0, const Launch& L) {
@@ -124,7 +151,9 @@ int launch_bwd_pipe(const Args& a, const Launch& L) {
     static const int cluster = env_int("LICV_PIPE_CLUSTER", 4);   // 1, 2, 4 or 8
     // a cluster launch and its two cluster barriers cost ~1 us: only worth it once enough CTAs
     // would otherwise queue on the same d_shift addresses
-    const int C = ((cluster == 2 || cluster == 4 || cluster == 8) && pa.n_batches > 32) ? cluster : 1;
+    const int C = (L.partial_rows == 0 && (cluster == 2 || cluster == 4 || cluster == 8) && pa.n_batches > 32)
+                      ? cluster
+                      : 1;
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(kPipeThreads);
     cfg.dynamicSmemBytes = smem;
@@ -155,6 +184,7 @@ int launch_bwd_pipe(const Args& a, const Launch& L) {
     if (tl_grid_cap > 0 && tl_grid_cap < lim) lim = tl_grid_cap;
     int64_t grid = pa.n_batches < lim ? pa.n_batches : lim;
     grid = (grid + C - 1) / C * C;
+    if (L.partial_rows > 0) grid = L.partial_rows;   // every row of the caller's block is written
     cfg.gridDim = dim3((unsigned)grid);
     return (int)cudaLaunchKernelEx(&cfg, kern, pa);
 }
@@ -166,8 +196,11 @@ int dispatch_bwd_pipe_tb(const Args& a, const Launch& L) {
     constexpr int TBbig = kFit >= 4 ? 4 : (kFit >= 2 ? 2 : 1);
     static const int forced_tb = env_int("LICV_PIPE_TB", 0);   // tuning knob: 1 = one token per stage
     const int64_t fill = (int64_t)device_info().sm_count * 2;
-    if (TBbig > 1 && forced_tb != 1 && (forced_tb > 1 || L.n_tok >= fill * TBbig))
-        return launch_bwd_pipe<HDT, GDT, VPT, TBbig, RND>(a, L);
+    // (spread mode ignores the tuning knob: pipe_partial_tb mirrors the plain rule)
+    const bool big = TBbig > 1 && (L.partial_rows > 0
+                                       ? L.n_tok >= fill * TBbig
+                                       : (forced_tb != 1 && (forced_tb > 1 || L.n_tok >= fill * TBbig)));
+    if (big) return launch_bwd_pipe<HDT, GDT, VPT, TBbig, RND>(a, L);
     return launch_bwd_pipe<HDT, GDT, VPT, 1, RND>(a, L);
 }
 

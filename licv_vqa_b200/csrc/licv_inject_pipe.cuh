@@ -271,6 +271,22 @@ __global__ void __launch_bounds__(kPipeThreads, 3) bwd_pipe_kernel(PipeArgs pa) 
     // thread-block cluster first sum their rows through distributed shared memory (CTA r of C
     // sums columns [r d/C, (r+1) d/C) of all C rows), then each issues REDG.F32x4 for its
     // columns only: C times fewer atomics.
+    // Spread mode: d_shift leaves as REDG.F32x4 into one of n_rows replicas of the [d] vector
+    // (replica = CTA index mod n_rows), added up later by licv_reduce_rows.  The L2 atomic units
+    // serialise per address (~27 clocks per contending warp): 256 CTAs on one [d] vector cost
+    // 3.5 us, which is what the cluster pre-reduction below buys back at the price of two cluster
+    // barriers; with <= 16 CTAs per replica the atomics are free and the CTA leaves at once.
+    if (a.rows != nullptr) {
+        float* row = a.rows + (int64_t)((int)blockIdx.x & a.row_mask) * (VPT * kPipeThreads * EPV);
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) {
+            const int j = tid + k * kPipeThreads;
+#pragma unroll
+            for (int e = 0; e < EPV; e += 4)
+                red_add_v4(row + (int64_t)j * EPV + e, ds[k][e], ds[k][e + 1], ds[k][e + 2], ds[k][e + 3]);
+        }
+        return;
+    }
     const uint32_t C = cluster_num_ctas();
     if (C == 1) {
 #pragma unroll

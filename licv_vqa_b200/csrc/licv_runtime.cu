@@ -95,6 +95,47 @@ icv_scale_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ 
     }
 }
 
+// out[l][c] (+)= sum_p rows[l][p][c]: one thread per (layer, 4 columns), the rows are L2-resident
+// (the backward launches of this step wrote them)
+__global__ void __launch_bounds__(256)
+reduce_rows_kernel(float* __restrict__ rows, float* __restrict__ out, int n_rows,
+                   int64_t layer_stride, int d, int64_t total4, int accumulate, int clear) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int d4 = d / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = i / d4;
+        const int c = (int)(i - l * d4);
+        float4* src = reinterpret_cast<float4*>(rows + l * layer_stride) + c;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int p = 0;
+        for (; p + 8 <= n_rows; p += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (int64_t)(p + u) * d4);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+            }
+        }
+        for (; p < n_rows; ++p) {
+            const float4 v = __ldcg(src + (int64_t)p * d4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        if (clear) {   // the replicas are ready for the next backward pass
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < n_rows; ++q) src[(int64_t)q * d4] = z;
+        }
+        float4* dst = reinterpret_cast<float4*>(out + l * d) + c;
+        if (accumulate) {
+            const float4 o = *dst;
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        *dst = acc;
+    }
+}
+
 __global__ void get_mask_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ len,
                                 int64_t pad, int batch, int seq, uint8_t* __restrict__ mask) {
     pdl_launch_dependents();
@@ -344,6 +385,25 @@ extern "C" int licv_icv_scale_bwd(const float* alpha_raw, const float* vec, cons
     return launch_pdl(icv_scale_bwd_kernel, dim3(n_layers), dim3(256), 0,
                       reinterpret_cast<cudaStream_t>(stream), alpha_raw, vec, d_icv, d_vec, d_alpha_raw,
                       d, use_sigmoid);
+}
+
+extern "C" int licv_reduce_rows(float* rows, float* out, int n_layers, int n_rows,
+                                int64_t layer_stride, int d, int accumulate, int clear,
+                                licv_stream_t stream) {
+    if (device_info().status != LICV_OK) return device_info().status;
+    if (n_layers < 0 || n_rows < 0 || d <= 0 || d % 4 != 0 || layer_stride % 4 != 0 ||
+        layer_stride < (int64_t)n_rows * d)
+        return LICV_ERR_BAD_DIM;
+    if (n_layers == 0) return LICV_OK;
+    if (!rows || !out) return LICV_ERR_NULL_POINTER;
+    if (!aligned16(rows) || !aligned16(out)) return LICV_ERR_MISALIGNED;
+    const int64_t total4 = (int64_t)n_layers * (d / 4);
+    int64_t grid = (total4 + 255) / 256;
+    const int64_t cap = (int64_t)device_info().sm_count * 8;
+    if (grid > cap) grid = cap;
+    return launch_pdl(reduce_rows_kernel, dim3((unsigned)grid), dim3(256), 0,
+                      reinterpret_cast<cudaStream_t>(stream), rows, out, n_rows, layer_stride, d, total4,
+                      accumulate, clear);
 }
 
 extern "C" int licv_get_mask(const int64_t* input_ids, const int64_t* mask_length,

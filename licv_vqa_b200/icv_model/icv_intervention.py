@@ -13,8 +13,10 @@ What is different underneath:
   installed ONCE; a call only swaps the active ICV state in and out;
 * the hook body (icv_intervention.py:61-86, five eager kernels + autograd's ~10 in backward + the
   retained clones) is one fused sm_100a kernel each way (`ops.inject`), saving only `h`;
-* the per-layer d_shift vectors are accumulated by the backward kernels straight into one
-  [L, d] fp32 buffer that becomes `icv.grad`'s source - no per-layer zero-padded index_put;
+* the per-layer d_shift partial sums are written by the backward kernels as plain rows of one
+  [L, P, d] fp32 block and added up by one launch when the last layer's backward has run - no
+  per-layer zero-padded index_put, no atomics, and the graph behind `icv` is walked once even
+  when reentrant activation checkpointing runs a nested backward per layer;
 * hooks stay armed with the call's ICV after `forward` returns, so activation-checkpoint
   recomputation during backward re-injects (the reference's context manager has already removed
   its hooks by then, icv_intervention.py:112-113).
@@ -34,7 +36,7 @@ from .. import ops
 class _ActiveICV:
     """The ICV of one forward/generate call, fanned out per hooked layer."""
 
-    __slots__ = ("icv", "shifts", "sink", "icv_dtype")
+    __slots__ = ("icv", "icv32", "shifts", "store", "icv_dtype", "anchor_layer")
 
     def __init__(self, icv: torch.Tensor):
         if icv.dim() != 3 or icv.shape[0] != 1:
@@ -43,8 +45,11 @@ class _ActiveICV:
         self.icv_dtype = icv.dtype
         # the kernels take the shift as fp32 (exact for bf16/fp16 ICVs); where the reference's
         # arithmetic would round because the ICV itself is low precision is carried by round_flags
-        icv32 = icv if icv.dtype == torch.float32 else icv.float()
-        self.shifts, self.sink = ops.fan_out_shifts(icv32.contiguous())
+        self.icv32 = (icv if icv.dtype == torch.float32 else icv.float()).contiguous()
+        # detached per-layer shifts + the store their backward kernels deposit d_shift in; the
+        # first hooked layer that runs carries the token that ties the store back to `icv`
+        self.shifts, self.store = ops.fan_out_shifts(self.icv32)
+        self.anchor_layer = None
 
 
 class LearnableICVInterventionLMM(nn.Module):
@@ -133,8 +138,20 @@ class LearnableICVInterventionLMM(nn.Module):
     def _inject(self, hidden_states, active: _ActiveICV, icv_index: int):
         flags, ref_dtype = ops.reference_rounding(hidden_states.dtype, active.icv_dtype)
         out_dtype = ref_dtype if self.residual_dtype == "promote" else hidden_states.dtype
-        return ops.inject(hidden_states, active.shifts[icv_index], out_dtype, flags,
-                          active.sink[icv_index])
+        shift = active.shifts[icv_index]
+        # The first hooked layer of the forward pass anchors the gradient store: its backward runs
+        # last.  Recorded even when grad mode is off - reentrant activation checkpointing runs
+        # the forward under no_grad and recomputes the layers, LAST layer first, during backward.
+        if active.icv32.requires_grad and active.anchor_layer is None:
+            active.anchor_layer = icv_index
+        if not active.icv32.requires_grad or not torch.is_grad_enabled():
+            return ops.inject(hidden_states, shift, out_dtype, flags)   # a fixed ICV: only dh, if any
+        # (the token is re-applied when checkpointing recomputes the anchor layer during backward)
+        token = None
+        if icv_index == active.anchor_layer:
+            token = ops.anchor_token(active.icv32, active.store)
+        return ops.inject_stored(hidden_states, shift, out_dtype, flags, active.store, icv_index,
+                                 token)
 
     def remove_hooks(self):
         """Detach from the tower (the wrapper then behaves as if intervention were disabled)."""

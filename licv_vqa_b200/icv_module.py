@@ -56,7 +56,10 @@ class ModuleConfig:
     # --- additions of this implementation (defaults keep the reference's semantics) ---
     ce_variant: str = "auto"            # "idefics" | "idefics2" | "causal_lm" | "auto" (by lmm name)
     image_token_id: int = -1            # idefics2: label id ignored by its CE
-    gradient_checkpointing: bool = False  # reference enables it whenever the tower supports it
+    # the reference enables activation checkpointing whenever the tower supports it
+    # (icv_module.py:29-30); "reentrant" / "non_reentrant" pick torch.utils.checkpoint's mode
+    # (True = the installed transformers' default), False turns it off
+    gradient_checkpointing: Any = True
     check_row_counts: bool = False      # True: sync and raise when the two masks select != rows
     residual_dtype: str = "promote"     # see LearnableICVInterventionLMM
     # f1: run lm_head on the teacher's SELECTED rows only (the reference materialises
@@ -101,9 +104,13 @@ class VQAICVModule(nn.Module):
         self.interface = interface
 
         self.interface.requires_grad_(False)
-        if _get(self.module_cfg, "gradient_checkpointing", False) and hasattr(
-                self.interface.model, "gradient_checkpointing_enable"):
-            self.interface.model.gradient_checkpointing_enable()
+        gc = _get(self.module_cfg, "gradient_checkpointing", True)
+        if gc and hasattr(self.interface.model, "gradient_checkpointing_enable"):
+            if gc in ("reentrant", "non_reentrant"):
+                self.interface.model.gradient_checkpointing_enable(
+                    gradient_checkpointing_kwargs={"use_reentrant": gc == "reentrant"})
+            else:
+                self.interface.model.gradient_checkpointing_enable()
 
         self.icv_model = LearnableICVInterventionLMM(
             interface,

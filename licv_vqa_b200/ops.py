@@ -169,40 +169,112 @@ def inject(h, shift, out_dtype=None, round_flags=0, sink_row=None):
     return _Inject.apply(h, shift, out_dtype, round_flags, sink_row)
 
 
-class _ShiftFanout(torch.autograd.Function):
-    """icv [1,L,d] -> L per-layer shift vectors.  Backward hands back the shared [L,d] sink the
-    per-layer injection backwards accumulated into - no stack/cat, no per-layer zero padding."""
+class GradStore:
+    """Where the per-layer injection backwards of a backward pass leave d_shift.
+
+    Every layer owns ``R`` fp32 replicas of its [d] gradient; the CTAs of its backward launch add
+    into replica ``cta mod R`` (``licv_inject_bwd_spread``: <= 16 CTAs per atomic address instead
+    of all of them on one vector), and ``collect`` adds up the replicas of all layers in one
+    launch that also zero-fills them for the next pass.  A layer that runs its backward twice in
+    a pass (or with other shapes) simply adds again."""
+
+    MAX_ROWS = 16
+
+    def __init__(self, n_layers: int, d: int, device):
+        self.L, self.d, self.device = n_layers, d, device
+        self.rows = None             # [L, R, d] replicas, zero between passes
+        self.r = 0
+        self.deposited = [False] * n_layers
+        self.expected = set()        # layers whose forward ran with a gradient wanted
+
+    def deposit(self, layer, h, g, shift, want_dh, round_flags):
+        lib = _abi.load()
+        d = self.d
+        hc, gc = h.contiguous(), g.contiguous()
+        n_tok = hc.numel() // d
+        dh = torch.empty_like(hc) if want_dh else None
+        if self.rows is None:
+            r = lib.licv_inject_bwd_rows(n_tok, d, _code(h.dtype), _code(g.dtype))
+            if r < 0:
+                _abi.check(r, "licv_inject_bwd_rows")
+            self.r = min(int(r), self.MAX_ROWS)
+            self.rows = torch.zeros(self.L, self.r, d, dtype=torch.float32, device=self.device)
+        _abi.check(lib.licv_inject_bwd_spread(
+            hc.data_ptr(), gc.data_ptr(), shift.data_ptr(), _ptr(dh), self.rows[layer].data_ptr(),
+            self.r, n_tok, d, _code(h.dtype), _code(g.dtype), round_flags, _stream()),
+            "licv_inject_bwd_spread")
+        self.deposited[layer] = True
+        return dh
+
+    def collect(self) -> torch.Tensor:
+        """-> d_shift of every layer, [L, d] fp32; the store is ready for the next pass."""
+        missing = [l for l in self.expected if not self.deposited[l]]
+        if missing:
+            raise RuntimeError(
+                f"ICV gradient collected before layers {missing} ran their backward: the hooked "
+                "layers are expected to run backward in the reverse of their forward order")
+        out = torch.empty(self.L, self.d, dtype=torch.float32, device=self.device)
+        if self.rows is None:
+            return out.zero_()
+        _abi.check(_abi.load().licv_reduce_rows(self.rows.data_ptr(), out.data_ptr(), self.L, self.r,
+                                                self.r * self.d, self.d, 0, 1, _stream()),
+                   "licv_reduce_rows")
+        self.deposited = [False] * self.L
+        self.expected = set()
+        return out
+
+
+class _Anchor(torch.autograd.Function):
+    """icv -> a 1-element token handed to the FIRST hooked layer's injection.  That layer runs its
+    backward last, so the token's gradient arrives when every layer has deposited its d_shift:
+    this node then collects them into d(icv).  The per-layer shifts themselves are detached - a
+    nested backward (reentrant activation checkpointing runs one per layer) only deposits, and
+    the graph behind ``icv`` (the encoder's alpha * v) is walked once."""
 
     @staticmethod
-    def forward(ctx, icv32, sink):
-        ctx.sink = sink
+    def forward(ctx, icv32, store):
+        ctx.store = store
         ctx.shape = icv32.shape
-        flat = icv32.reshape(icv32.shape[-2], icv32.shape[-1])
-        return tuple(flat[l] for l in range(flat.shape[0]))
+        return torch.zeros(1, dtype=torch.float32, device=icv32.device)
 
     @staticmethod
-    def backward(ctx, *grads):
-        sink = ctx.sink
-        # zero-copy only for a full backward in which every layer's gradient IS its sink row; a
-        # partial call (reentrant checkpointing runs one nested backward per layer) is summed
-        # by autograd from per-call tensors instead
-        direct = all(g is not None and g.data_ptr() == sink[l].data_ptr() and g.dtype == sink.dtype
-                     for l, g in enumerate(grads))
-        if direct:
-            return sink.view(ctx.shape), None
-        rows = [torch.zeros_like(sink[l]) if g is None else g.to(sink.dtype)
-                for l, g in enumerate(grads)]
-        return torch.stack(rows).view(ctx.shape), None
+    def backward(ctx, _g):
+        return ctx.store.collect().view(ctx.shape), None
+
+
+class _InjectStored(torch.autograd.Function):
+    """The hook's injection: h -> out, d_shift deposited in a GradStore (see _Anchor)."""
+
+    @staticmethod
+    def forward(ctx, h, shift, out_dtype, round_flags, store, layer, token):
+        out = inject_forward(h, shift, out_dtype, round_flags)
+        ctx.save_for_backward(h, shift)
+        ctx.round_flags, ctx.store, ctx.layer = round_flags, store, layer
+        ctx.has_token = token is not None
+        store.expected.add(layer)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, shift = ctx.saved_tensors
+        dh = ctx.store.deposit(ctx.layer, h, g, shift, ctx.needs_input_grad[0], ctx.round_flags)
+        token_grad = torch.zeros(1, dtype=torch.float32, device=g.device) if ctx.has_token else None
+        return dh, None, None, None, None, None, token_grad
+
+
+def inject_stored(h, shift, out_dtype, round_flags, store, layer, token):
+    return _InjectStored.apply(h, shift, out_dtype, round_flags, store, layer, token)
 
 
 def fan_out_shifts(icv32: torch.Tensor):
-    """-> (tuple of L shift vectors [d], sink [L,d] fp32 zeros)."""
+    """-> (tuple of L detached shift vectors [d], GradStore)."""
     L, d = icv32.shape[-2], icv32.shape[-1]
-    sink = torch.zeros(L, d, dtype=torch.float32, device=icv32.device)
-    if torch.is_grad_enabled() and icv32.requires_grad:
-        return _ShiftFanout.apply(icv32, sink), sink
-    flat = icv32.reshape(L, d)
-    return tuple(flat[l] for l in range(L)), sink
+    flat = icv32.detach().reshape(L, d)
+    return tuple(flat[l] for l in range(L)), GradStore(L, d, icv32.device)
+
+
+def anchor_token(icv32: torch.Tensor, store: GradStore) -> torch.Tensor:
+    return _Anchor.apply(icv32, store)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -264,3 +264,42 @@ def test_inject_baseline_config_shapes(ops, name, n_tok, hdt, chain):
     o_dh, o_ds = O.inject_bwd(hn, host(shift), host(g), flags, hdt if flags else None)
     assert rel_err(host(ds), o_ds) < 1e-4                      # stated: 1e-4 with fp32 accumulation
     assert rel_err(host(dh), o_dh) < 1.2 * EPS[hdt]
+
+
+@pytest.mark.parametrize("n_tok,d,hdt", [(256, 4096, "fp16"), (256, 4096, "bf16"), (24, 4096, "bf16"),
+                                         (1000, 2048, "fp32"), (5000, 4096, "bf16"), (77, 1536, "bf16")])
+def test_inject_backward_spread_replicas_equal_accumulated(ops, n_tok, d, hdt):
+    """licv_inject_bwd_spread + licv_reduce_rows against licv_inject_bwd on the same launch: dh
+    bit-identical, d_shift equal up to the summation order (fp32, 1e-6)."""
+    from licv_vqa_b200 import _abi
+    lib = _abi.load()
+    torch.manual_seed(n_tok + d)
+    dt = TD[hdt]
+    h = (torch.randn(n_tok, d, device="cuda") * 4).to(dt)
+    g = torch.randn(n_tok, d, device="cuda").to(dt)
+    shift = torch.randn(d, device="cuda")
+    ds = torch.zeros(d, device="cuda")
+    dh = ops.inject_backward(h, g, shift, ds, True, 0)
+    code = {"fp32": _abi.F32, "bf16": _abi.BF16, "fp16": _abi.F16}[hdt]
+    st = torch.cuda.current_stream().cuda_stream
+    R = lib.licv_inject_bwd_rows(n_tok, d, code, code)
+    assert 1 <= R <= 16 and R & (R - 1) == 0
+    rows = torch.zeros(3, R, d, device="cuda")
+    dh2 = torch.empty_like(h)
+    _abi.check(lib.licv_inject_bwd_spread(h.data_ptr(), g.data_ptr(), shift.data_ptr(), dh2.data_ptr(),
+                                          rows[1].data_ptr(), R, n_tok, d, code, code, 0, st))
+    assert torch.equal(dh, dh2)
+    assert not rows[0].any() and not rows[2].any()
+    if R > 1 and n_tok >= 64:
+        assert bool(rows[1, R - 1].any())            # the CTAs really spread over the replicas
+    out = torch.zeros(3, d, device="cuda")
+    _abi.check(lib.licv_reduce_rows(rows[1].data_ptr(), out[1].data_ptr(), 1, R, R * d, d, 0, 0, st))
+    assert rel_err(host(out[1]), host(ds)) < 1e-6
+    assert not out[0].any() and not out[2].any()
+    # a second launch (another micro-batch, or the same layer again) adds; the reduce can
+    # accumulate into its output and leaves the replicas zero for the next pass
+    _abi.check(lib.licv_inject_bwd_spread(h.data_ptr(), g.data_ptr(), shift.data_ptr(), 0,
+                                          rows[1].data_ptr(), R, n_tok, d, code, code, 0, st))
+    _abi.check(lib.licv_reduce_rows(rows[1].data_ptr(), out[1].data_ptr(), 1, R, R * d, d, 1, 1, st))
+    assert rel_err(host(out[1]), 3 * host(ds)) < 1e-6
+    assert not rows[1].any()

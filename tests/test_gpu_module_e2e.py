@@ -175,3 +175,44 @@ def test_hook_points_match_eager_torch_hooks(tower, layer_format, layers):
     assert abs(got[1] - float(so.loss)) <= 1e-4 * abs(float(so.loss))
     assert rel_err(got[2].cpu().numpy(), icv_p.grad.cpu().numpy()) < 1e-4
     assert rel_err(got[3].cpu().numpy(), alpha.grad.cpu().numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("mode", ["reentrant", "non_reentrant"])
+def test_gradient_checkpointing_gives_the_same_icv_gradients(tower, mode):
+    """The reference enables activation checkpointing whenever the tower supports it
+    (icv_module.py:29-30).  Reentrant checkpointing runs a nested backward per layer during the
+    outer backward; the hooks stay armed so the recomputation re-injects, the per-layer backwards
+    only deposit their d_shift, and the graph behind `icv` is walked once."""
+    from licv_vqa_b200 import LMMConfig, ModuleConfig, VQAICVModule
+    from licv_vqa_b200.icv_module import ICVEncoderConfig
+    dev = "cuda"
+    q = {"input_ids": torch.tensor(G["q_ids"]).to(dev), "attention_mask": torch.tensor(G["q_att"]).to(dev)}
+    t = {"input_ids": torch.tensor(G["t_ids"]).to(dev), "attention_mask": torch.tensor(G["t_att"]).to(dev)}
+    qxl = torch.tensor(G["query_x_length"]).to(dev)
+    icl = torch.tensor(G["in_context_length"]).to(dev)
+    gen = torch.Generator().manual_seed(5)
+    vec = torch.randn(1, 2, 512, generator=gen) * 0.5
+    results = {}
+    for gc in (False, mode):
+        cfg = ModuleConfig(hard_loss_weight=0.5, kl_eps=1e-6, ce_variant="causal_lm",
+                           gradient_checkpointing=gc,
+                           icv_encoder=ICVEncoderConfig(use_sigmoid=True, alpha_init_value=0.3))
+        tower.gradient_checkpointing_disable()
+        mod = VQAICVModule(Interface(tower), cfg, LMMConfig("tiny", 2, "model.model.layers.<LAYER_NUM>", -1, 512)).cuda()
+        tower.train()      # HF checkpoints only in training mode
+        assert tower.is_gradient_checkpointing == bool(gc)
+        with torch.no_grad():
+            mod.icv_encoder.icv.copy_(vec)
+        for _ in range(2):        # two steps: the store is reusable after a collect
+            mod.zero_grad(set_to_none=True)
+            loss_dict, _ = mod(q, t, qxl, icl)
+            loss_dict["loss"].backward()
+        results[gc] = (float(loss_dict["loss"]), mod.icv_encoder.icv.grad.clone(),
+                       mod.icv_encoder.alpha.grad.clone())
+        mod.icv_model.remove_hooks()
+    tower.gradient_checkpointing_disable()
+    tower.eval()
+    ref, got = results[False], results[mode]
+    assert abs(ref[0] - got[0]) <= 1e-6 * abs(ref[0])
+    assert rel_err(got[1].cpu().numpy(), ref[1].cpu().numpy()) < 1e-5
+    assert rel_err(got[2].cpu().numpy(), ref[2].cpu().numpy()) < 1e-5

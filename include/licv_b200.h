@@ -242,8 +242,11 @@ int licv_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_
  *   are updated with the mean gradient (clip at max_grad_norm, AdamW).  Two launches, no host
  *   synchronisation, replayable from a CUDA graph (the step counter lives in device memory).
  *   world == 1 degenerates to licv_adamw_step.  A region holds two slots per possible source
- *   rank (16) of 16-byte {3 floats, step tag} packets: about 22 MB for idefics shapes.  Every
- *   rank must call once per step, with the same step number.
+ *   rank (16) of 16-byte {float, step tag, float, step tag} packets (each 8-byte half guarded by
+ *   its own tag): about 34 MB for idefics shapes.  Every rank must call once per step.  A peer
+ *   that never delivers (~4 s) raises the error flag: that step's optimizer update is SKIPPED on
+ *   this rank (parameters, moments and the local gradient stay as they were) and every later
+ *   step too, until licv_dp_comm_reset_error.
  * ------------------------------------------------------------------------------------------ */
 typedef struct licv_dp_comm licv_dp_comm;
 int64_t licv_dp_region_bytes(int64_t n_floats);
@@ -251,7 +254,9 @@ int licv_dp_region_alloc(int64_t n_floats, void** region, void* ipc_handle_64);
 int licv_dp_comm_create(licv_dp_comm** out, int rank, int world, void* region,
                         const void* all_handles /* world x 64 bytes, rank order */, int64_t n_floats);
 int licv_dp_comm_destroy(licv_dp_comm* c);
-int licv_dp_comm_error(licv_dp_comm* c); /* 1 if a wait for a peer ever timed out */
+int licv_dp_comm_error(licv_dp_comm* c); /* 1 if a wait for a peer ever timed out (synchronises) */
+int licv_dp_comm_reset_error(licv_dp_comm* c);
+int licv_dp_region_free(void* region);    /* a region that never made it into a comm */
 int licv_dp_allreduce_adamw(licv_dp_comm* c, float* param, float* grad, float* exp_avg,
                             float* exp_avg_sq, int64_t n_vec, int64_t n_alpha, int64_t n_extra,
                             float lr_vec, float lr_alpha, float beta1, float beta2, float eps,

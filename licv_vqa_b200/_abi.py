@@ -52,6 +52,8 @@ SIGNATURES = {
     "licv_dp_comm_create": (_i32, [C.POINTER(_vp), _i32, _i32, _vp, _vp, _i64]),
     "licv_dp_comm_destroy": (_i32, [_vp]),
     "licv_dp_comm_error": (_i32, [_vp]),
+    "licv_dp_comm_reset_error": (_i32, [_vp]),
+    "licv_dp_region_free": (_i32, [_vp]),
     "licv_dp_allreduce_adamw": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _f32, _f32,
                                        _f32, _f32, _f32, _i64, _f32, _vp, _vp, _vp]),
     "licv_host_session_create": (_i32, [C.POINTER(_vp), _i64, _i32]),

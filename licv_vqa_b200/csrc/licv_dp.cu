@@ -9,17 +9,19 @@
 // that all peers map (CUDA IPC), and ONE kernel does the whole exchange with no flag, fence,
 // ticket or barrier on the way:
 //
-//   push    each thread packs three gradient floats and the step number into one 16-byte packet
-//           {f0, f1, f2, tag} and stores it into the slot [step parity][this rank] of EVERY
-//           peer's region (posted writes over NVLink, one per peer, back to back);
+//   push    each thread packs two gradient floats, each with the step number, into one 16-byte
+//           packet {f0, tag, f1, tag} and stores it (st.v2.b64) into the slot [step parity][this
+//           rank] of EVERY peer's region (posted writes over NVLink, one per peer, back to back);
 //   gather  the same thread reads the packets the peers pushed at the same index into its own
 //           region - local memory - until each carries this step's tag, sums the values in
 //           RANK ORDER (every rank gets bit-identical sums), writes the sum back as the
 //           gradient and accumulates its squared norm for the clip,
 //
-// and the existing AdamW kernel follows on the same stream.  The tag travels inside the same
-// aligned 16-byte store as the data it guards (the idea of NCCL's LL protocols), so a packet is
-// either absent or complete: the latency of the exchange is ONE one-way trip of posted writes
+// and the existing AdamW kernel follows on the same stream.  Every 8-byte half of a packet carries
+// its own copy of the tag next to the float it guards - NCCL's LL protocol: the PTX memory model
+// treats a vector access as one scalar access per element, an aligned 8-byte element is
+// single-copy atomic, and the reader accepts a packet only when BOTH halves show this step's tag
+// - so a half is either absent or complete and the latency of the exchange is ONE one-way trip
 // instead of copy -> system fence -> flag -> flag seen -> remote read round trip (measured, two
 // ranks, CTA 0: 1.4 + 3.5 + 6.5 + 4.3 us for those four).  Two slots per source alternate by step
 // parity: a peer can only push step k + 2 after it has finished step k + 1, which needed this
@@ -37,7 +39,7 @@ int launch_adamw_after_norm(float* param, const float* grad, float* exp_avg, flo
                             float beta2, float eps, float weight_decay, int64_t step,
                             float grad_prescale, float max_grad_norm, float* norm_out,
                             void* workspace, const float* norm_partials, int n_partials,
-                            cudaStream_t st);
+                            const unsigned* skip_if_set, cudaStream_t st);
 }
 
 constexpr int kDpMaxWorld = 16;
@@ -59,7 +61,7 @@ struct Layout {
 };
 Layout layout_of(int64_t n) {
     Layout L;
-    L.n_packets = (n + 2) / 3;
+    L.n_packets = (n + 1) / 2;
     L.slot_bytes = ((L.n_packets * 16 + 255) / 256) * 256;
     L.ctl_off = 2 * kDpMaxWorld * L.slot_bytes;
     L.partial_off = L.ctl_off + 64;
@@ -84,18 +86,18 @@ struct DpArgs {
     float* partial;       // [gridDim.x] per-CTA sums of squares (summed in fixed order later)
 };
 
-__device__ __forceinline__ void st_packet(void* p, uint4 v) {
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
-                 "r"(v.w)
-                 : "memory");
+// one packet = two 8-byte elements {float bits | tag << 32}: each element is one scalar access
+__device__ __forceinline__ void st_packet(void* p, unsigned long long lo, unsigned long long hi) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(lo), "l"(hi) : "memory");
 }
-__device__ __forceinline__ uint4 ld_packet(const void* p) {
-    uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p)
-                 : "memory");
-    return v;
+__device__ __forceinline__ void ld_packet(const void* p, unsigned long long& lo, unsigned long long& hi) {
+    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned long long half_packet(float f, unsigned tag) {
+    return (unsigned long long)__float_as_uint(f) | ((unsigned long long)tag << 32);
+}
+__device__ __forceinline__ bool packet_ok(unsigned long long lo, unsigned long long hi, unsigned tag) {
+    return (unsigned)(lo >> 32) == tag && (unsigned)(hi >> 32) == tag;
 }
 
 #ifdef LICV_TRACE
@@ -136,54 +138,56 @@ __global__ void __launch_bounds__(kDpThreads) dp_exchange_kernel(DpArgs a) {
     const int tid = threadIdx.x;
 
     float sq = 0.f;
+    bool dead = false;        // a peer never delivered: this rank must not apply the step
     for (int64_t i = (int64_t)blockIdx.x * kDpThreads + tid; i < a.n_packets;
          i += (int64_t)gridDim.x * kDpThreads) {
-        float f[3];
+        float f[2];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) f[k] = i * 3 + k < a.n ? a.grad[i * 3 + k] : 0.f;
+        for (int k = 0; k < 2; ++k) f[k] = i * 2 + k < a.n ? a.grad[i * 2 + k] : 0.f;
         // ---- push: one posted 16-byte write per peer ------------------------------------------
-        const uint4 pk = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), tag);
+        const unsigned long long plo = half_packet(f[0], tag), phi = half_packet(f[1], tag);
 #pragma unroll
         for (int p = 0; p < kDpMaxWorld; ++p)
-            if (p < a.world && p != a.rank) st_packet(a.region[p] + my_slot + i * 16, pk);
+            if (p < a.world && p != a.rank) st_packet(a.region[p] + my_slot + i * 16, plo, phi);
         DP_TP(2);
         // ---- gather: the peers' packets at the same index, from LOCAL memory ------------------
-        uint4 v[kDpMaxWorld];
+        unsigned long long vlo[kDpMaxWorld], vhi[kDpMaxWorld];
 #pragma unroll
         for (int p = 0; p < kDpMaxWorld; ++p)
             if (p < a.world && p != a.rank)
-                v[p] = ld_packet(local + parity_off + (int64_t)p * a.slot_bytes + i * 16);
+                ld_packet(local + parity_off + (int64_t)p * a.slot_bytes + i * 16, vlo[p], vhi[p]);
 #pragma unroll
         for (int p = 0; p < kDpMaxWorld; ++p) {
-            if (p < a.world && p != a.rank && v[p].w != tag) {
+            if (p < a.world && p != a.rank && !packet_ok(vlo[p], vhi[p], tag)) {
                 const long long t0 = clock64();
                 do {                                   // bounded: a dead peer must not hang us
-                    v[p] = ld_packet(local + parity_off + (int64_t)p * a.slot_bytes + i * 16);
+                    ld_packet(local + parity_off + (int64_t)p * a.slot_bytes + i * 16, vlo[p], vhi[p]);
                     if (clock64() - t0 > (1ll << 33)) {   // ~4 s
                         *error = 1u;
+                        dead = true;
                         break;
                     }
-                } while (v[p].w != tag);
+                } while (!packet_ok(vlo[p], vhi[p], tag));
             }
         }
         DP_TP(3);
-        float s[3] = {0.f, 0.f, 0.f};
+        if (dead) continue;    // keep the local gradient; the optimizer kernel is skipped (error flag)
+        float s[2] = {0.f, 0.f};
 #pragma unroll
         for (int p = 0; p < kDpMaxWorld; ++p) {
             if (p < a.world) {
                 if (p == a.rank) {
-                    s[0] += f[0]; s[1] += f[1]; s[2] += f[2];
+                    s[0] += f[0]; s[1] += f[1];
                 } else {
-                    s[0] += __uint_as_float(v[p].x);
-                    s[1] += __uint_as_float(v[p].y);
-                    s[2] += __uint_as_float(v[p].z);
+                    s[0] += __uint_as_float((unsigned)vlo[p]);
+                    s[1] += __uint_as_float((unsigned)vhi[p]);
                 }
             }
         }
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            if (i * 3 + k < a.n) a.grad[i * 3 + k] = s[k];
-            if (i * 3 + k < a.n_norm) {
+        for (int k = 0; k < 2; ++k) {
+            if (i * 2 + k < a.n) a.grad[i * 2 + k] = s[k];
+            if (i * 2 + k < a.n_norm) {
                 const float x = s[k] * a.prescale;
                 sq = fmaf(x, x, sq);
             }
@@ -244,6 +248,11 @@ extern "C" int licv_dp_region_alloc(int64_t n_floats, void** region, void* ipc_h
     return LICV_OK;
 }
 
+extern "C" int licv_dp_region_free(void* region) {
+    if (!region) return LICV_OK;
+    return (int)cudaFree(region);
+}
+
 extern "C" int licv_dp_comm_create(licv_dp_comm** out, int rank, int world, void* region,
                                    const void* all_handles, int64_t n_floats) {
     if (!out || !region) return LICV_ERR_NULL_POINTER;
@@ -295,6 +304,13 @@ extern "C" int licv_dp_comm_error(licv_dp_comm* c) {
     return (int)err;
 }
 
+extern "C" int licv_dp_comm_reset_error(licv_dp_comm* c) {
+    if (!c) return LICV_ERR_NULL_POINTER;
+    const Layout L = layout_of(c->n);
+    if (cudaMemset(c->region[c->rank] + L.ctl_off + 16, 0, 4) != cudaSuccess) return (int)cudaGetLastError();
+    return LICV_OK;
+}
+
 extern "C" int licv_dp_allreduce_adamw(licv_dp_comm* c, float* param, float* grad, float* exp_avg,
                                        float* exp_avg_sq, int64_t n_vec, int64_t n_alpha,
                                        int64_t n_extra, float lr_vec, float lr_alpha, float beta1,
@@ -327,5 +343,7 @@ extern "C" int licv_dp_allreduce_adamw(licv_dp_comm* c, float* param, float* gra
     return licv::launch_adamw_after_norm(param, grad, exp_avg, exp_avg_sq, n_vec, n_alpha, lr_vec,
                                          lr_alpha, beta1, beta2, eps, weight_decay, step,
                                          1.0f / (float)c->world, max_grad_norm, norm_out, workspace,
-                                         a.partial, grid, st);
+                                         a.partial, grid,
+                                         reinterpret_cast<const unsigned*>(c->region[c->rank] + L.ctl_off + 16),
+                                         st);
 }

@@ -281,11 +281,14 @@ struct AdamArgs {
     unsigned* ticket;      // workspace[1]
     const float* partials; // or: n_partials sums of squares to be added in index order
     int n_partials;
+    const unsigned* skip;  // if set and non-zero: the gradient is not trustworthy, leave everything as it is
 };
 
 __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
     pdl_launch_dependents();
     pdl_wait();
+    // a failed gradient exchange (a peer never delivered) must not move the parameters
+    if (a.skip != nullptr && *reinterpret_cast<const volatile unsigned*>(a.skip) != 0u) return;
     // every CTA reads the norm before taking a ticket; the last ticket holder clears the workspace
     float coef = a.prescale;
     float sumsq;
@@ -468,11 +471,12 @@ int launch_adamw_after_norm(float* param, const float* grad, float* exp_avg, flo
                             float beta2, float eps, float weight_decay, int64_t step,
                             float grad_prescale, float max_grad_norm, float* norm_out,
                             void* workspace, const float* norm_partials, int n_partials,
-                            cudaStream_t st) {
+                            const unsigned* skip_if_set, cudaStream_t st) {
     const int64_t n = n_vec + n_alpha;
     AdamArgs a;
     a.partials = norm_partials;
     a.n_partials = n_partials;
+    a.skip = skip_if_set;
     a.p = param; a.g = grad; a.m = exp_avg; a.v = exp_avg_sq;
     a.n_vec = n_vec; a.n_alpha = n_alpha;
     a.lr_vec = lr_vec; a.lr_alpha = lr_alpha; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
@@ -504,5 +508,5 @@ extern "C" int licv_adamw_step(float* param, const float* grad, float* exp_avg, 
         return rc;
     return launch_adamw_after_norm(param, grad, exp_avg, exp_avg_sq, n_vec, n_alpha, lr_vec, lr_alpha,
                                    beta1, beta2, eps, weight_decay, step, grad_prescale,
-                                   max_grad_norm, norm_out, workspace, nullptr, 0, st);
+                                   max_grad_norm, norm_out, workspace, nullptr, 0, nullptr, st);
 }

@@ -99,13 +99,24 @@ class FlatICVState:
         return self.grad[self.n:self.n + N_SCALARS]
 
     def rebind(self):
-        """Re-attach the gradient views (after `zero_grad(set_to_none=True)` or similar)."""
+        """Re-attach the gradient views.  After `module.zero_grad()` (set_to_none=True is torch's
+        default) autograd has created FRESH `.grad` tensors: what they hold is this step's
+        gradient and is added into the flat buffer before the views are put back - dropping it
+        would make the next optimizer step a weight-decay-only step."""
         enc = self.encoder
-        if enc.icv.grad is None or enc.icv.grad.data_ptr() != self.grad.data_ptr():
-            enc.icv.grad = self.grad[:self.n_vec].view(enc.icv.shape)
-        if self.alpha_learnable and (enc.alpha.grad is None or
-                                     enc.alpha.grad.data_ptr() != self.grad[self.n_vec:].data_ptr()):
-            enc.alpha.grad = self.grad[self.n_vec:self.n].view(enc.alpha.shape)
+        flat_v = self.grad[:self.n_vec].view(enc.icv.shape)
+        g = enc.icv.grad
+        if g is None or g.data_ptr() != flat_v.data_ptr():
+            if g is not None:
+                flat_v.add_(g.to(flat_v.dtype))
+            enc.icv.grad = flat_v
+        if self.alpha_learnable:
+            flat_a = self.grad[self.n_vec:self.n].view(enc.alpha.shape)
+            g = enc.alpha.grad
+            if g is None or g.data_ptr() != flat_a.data_ptr():
+                if g is not None:
+                    flat_a.add_(g.to(flat_a.dtype))
+                enc.alpha.grad = flat_a
 
     def zero_grad(self):
         self.grad.zero_()
@@ -121,6 +132,8 @@ class PeerExchange:
     launches and no collective call."""
 
     def __init__(self, n_floats: int, group=None):
+        """Collective over `group`: raises on EVERY rank if the set-up failed on any of them (one
+        rank falling back to NCCL on its own would leave the others spinning on its packets)."""
         import ctypes as C
 
         from . import _abi
@@ -130,8 +143,30 @@ class PeerExchange:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.n = int(n_floats)
+        self.comm = None
         region, handle = C.c_void_p(), C.create_string_buffer(64)
-        _abi.check(self.lib.licv_dp_region_alloc(self.n, C.byref(region), handle), "licv_dp_region_alloc")
+        failure = None
+
+        def agree(stage):
+            """MIN over ranks of 'I am fine so far' - every rank takes the same branch."""
+            nonlocal failure
+            if self.world == 1:
+                ok = failure is None
+            else:
+                flag = torch.tensor([0.0 if failure else 1.0], device="cuda")
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+                ok = bool(flag.item() == 1.0)
+            if not ok:
+                if region:
+                    self.lib.licv_dp_region_free(region)
+                raise RuntimeError(f"peer-memory exchange unavailable ({stage}): "
+                                   f"{failure or 'another rank failed'}")
+
+        rc = self.lib.licv_dp_region_alloc(self.n, C.byref(region), handle)
+        if rc != 0:
+            failure = f"licv_dp_region_alloc: {_abi.status_string(rc)}"
+            region = C.c_void_p()
+        agree("region")
         handles = handle.raw
         if self.world > 1:
             mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).cuda()
@@ -140,11 +175,12 @@ class PeerExchange:
             handles = b"".join(bytes(t.cpu().tolist()) for t in every)
         self._handles = C.create_string_buffer(handles, len(handles))
         comm = C.c_void_p()
-        _abi.check(self.lib.licv_dp_comm_create(C.byref(comm), self.rank, self.world, region,
-                                                self._handles, self.n), "licv_dp_comm_create")
+        rc = self.lib.licv_dp_comm_create(C.byref(comm), self.rank, self.world, region,
+                                          self._handles, self.n)
+        if rc != 0:
+            failure = f"licv_dp_comm_create: {_abi.status_string(rc)}"
+        agree("mapping the peers")     # also the barrier: every region is mapped before the first step
         self.comm = comm
-        if self.world > 1:
-            dist.barrier(group=group)     # every rank has mapped every region before the first step
 
     def step(self, param, grad, exp_avg, exp_avg_sq, n_vec, n_alpha, n_extra, lr_vec, lr_alpha,
              betas, eps, weight_decay, step, max_grad_norm, norm_out, workspace):
@@ -156,7 +192,11 @@ class PeerExchange:
             "licv_dp_allreduce_adamw")
 
     def timed_out(self) -> bool:
+        """Has a wait for a peer ever timed out?  Synchronises the device (a 4-byte read)."""
         return self.lib.licv_dp_comm_error(self.comm) == 1
+
+    def reset_error(self):
+        self._abi.check(self.lib.licv_dp_comm_reset_error(self.comm), "licv_dp_comm_reset_error")
 
     def close(self):
         if getattr(self, "comm", None) is not None and self.comm:
@@ -177,10 +217,13 @@ class ICVDataParallelOptimizer:
 
     def __init__(self, encoder: torch.nn.Module, module_cfg=None, total_steps: int = 1,
                  max_grad_norm: float = 1.0, process_group=None, betas=(0.9, 0.999),
-                 eps: float = 1e-8, exchange: str = "auto"):
+                 eps: float = 1e-8, exchange: str = "auto", check_every: int = 50):
         """``exchange``: "p2p" = fused exchange + optimizer over NVLink peer memory (one node),
         "nccl" = `all_reduce` then the optimizer kernels, "auto" = p2p for CUDA parameters in a
-        multi-rank group when the peers can be mapped, else nccl."""
+        multi-rank group when EVERY rank can map its peers (decided collectively), else nccl.
+        ``check_every``: the peer exchange's error flag (a peer that never delivered: the
+        optimizer update is skipped on the device) is polled every that many steps - a 4-byte
+        read that synchronises - and raises."""
         def get(name, default):
             if module_cfg is None:
                 return default
@@ -205,10 +248,12 @@ class ICVDataParallelOptimizer:
         self.peer = None
         if exchange not in ("auto", "p2p", "nccl"):
             raise ValueError("exchange must be 'auto', 'p2p' or 'nccl'")
+        self.check_every = int(check_every)
         if exchange != "nccl" and dev.type == "cuda" and self.world_size > 1:
             try:
+                # collective: either every rank gets the peer path or every rank raises here
                 self.peer = PeerExchange(self.state.grad.numel(), process_group)
-            except Exception:
+            except RuntimeError:
                 if exchange == "p2p":
                     raise
                 self.peer = None
@@ -269,6 +314,11 @@ class ICVDataParallelOptimizer:
                            self.max_grad_norm, self.grad_norm, self._ws)
             logs = {k: v.clone() for k, v in self.synced_logs().items()} if logged else {}
             self.zero_grad()
+            if self.check_every > 0 and self.step_no % self.check_every == 0 and self.peer.timed_out():
+                raise RuntimeError(
+                    "ICV gradient exchange: a peer did not deliver its gradient within ~4 s; the "
+                    "optimizer updates since then were skipped on this rank (PeerExchange.reset_error "
+                    "re-arms it once the ranks are back in step)")
             return logs
         self.all_reduce_gradients(logged)
         self.step_no += 1

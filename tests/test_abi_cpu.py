@@ -55,7 +55,7 @@ def test_no_device_is_an_error_not_a_fallback():
 
 def test_exchange_region_holds_two_packet_slots_per_source_rank():
     """licv_dp_region_bytes is host arithmetic: 2 parities x 16 possible source ranks x one 16-byte
-    {3 floats, tag} packet per three gradient floats (slots rounded to 256 B), plus the control
+    {float, tag, float, tag} packet per two gradient floats (slots rounded to 256 B), plus the control
     block and the per-CTA norm partials.  It must grow with the gradient and never be smaller than
     the packets it has to hold."""
     lib = _abi.load()
@@ -64,7 +64,7 @@ def test_exchange_region_holds_two_packet_slots_per_source_rank():
     for n in (1, 3, 4, 1000, 32 * 4096 + 32 + 4):
         got = lib.licv_dp_region_bytes(n)
         padded = (n + 3) // 4 * 4                     # FlatICVState pads the gradient to 4 floats
-        packets = (padded + 2) // 3
+        packets = (padded + 1) // 2
         slot = (packets * 16 + 255) // 256 * 256
         assert got >= 2 * 16 * slot + 64
         assert got <= 2 * 16 * slot + 64 + 4096

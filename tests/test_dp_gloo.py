@@ -130,3 +130,25 @@ def test_schedule_matches_oracle_and_frozen_alpha():
     assert float(enc.alpha.mean()) == pytest.approx(0.2)
     st.zero_grad()
     assert enc.icv.grad.data_ptr() == st.grad.data_ptr()
+
+
+def test_rebind_keeps_gradients_that_autograd_put_in_fresh_tensors():
+    """`module.zero_grad()` (set_to_none=True by default) detaches the flat views; the next
+    backward then creates fresh `.grad` tensors.  The optimizer must add those into the flat
+    buffer when it re-attaches its views - not drop them."""
+    torch.manual_seed(1)
+    enc = GlobalICVEncoder(D, L, alpha_learnable=True, alpha_init_value=0.1)
+    st = FlatICVState(enc)
+    gv, ga = _rank_grads(0)
+    enc.zero_grad(set_to_none=True)                      # what torch users do
+    assert enc.icv.grad is None
+    ((enc.icv * gv).sum() + (enc.alpha * ga).sum()).backward()
+    assert enc.icv.grad.data_ptr() != st.grad.data_ptr()   # autograd made its own tensors
+    st.rebind()
+    assert enc.icv.grad.data_ptr() == st.grad.data_ptr()
+    assert torch.allclose(st.grad[:st.n_vec].view(1, L, D), gv)
+    assert torch.allclose(st.grad[st.n_vec:st.n].view(1, L), ga)
+    # with the views attached, further backwards accumulate in place
+    ((enc.icv * gv).sum() + (enc.alpha * ga).sum()).backward()
+    st.rebind()
+    assert torch.allclose(st.grad[:st.n_vec].view(1, L, D), 2 * gv)

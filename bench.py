@@ -52,6 +52,12 @@ CFG = dict(workload="configs[1]: idefics-9B shape, VQAv2 32-shot teacher vs zero
            alpha_init_value=0.1, dtype="fp16", recipe="DeepSpeed 16-mixed (fp16 ICV, no autocast)")
 
 
+def config_of(n_gpus):
+    """The `config` of the JSON line: the SAME dict for this arm and for --impl reference."""
+    return dict(CFG, global_batch=CFG["batch_per_gpu"] * n_gpus, parallelism=f"dp{n_gpus}",
+                flush="inputs of one step (~290 MB, a distinct buffer per layer) exceed L2")
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -219,7 +225,9 @@ class HotPath:
         if rc != 0:
             self.abi.check(rc, what)
 
-    def step(self, batch, allreduce=True):
+    def compute(self, batch):
+        """icv -> 32 x inject fwd -> row prep + loss fwd/bwd -> 32 x inject bwd -> d_vec, d_alpha
+        (this rank's gradient in self.grad, logged scalars in its tail)."""
         lib, st = self.lib, torch.cuda.current_stream().cuda_stream
         L, d, V = CFG["layers"], CFG["d"], CFG["vocab"]
         B, T = CFG["batch_per_gpu"], CFG["student_tokens"]
@@ -256,22 +264,31 @@ class HotPath:
         self._chk(lib.licv_icv_scale_bwd(alpha_p, vec_p, self.sink.data_ptr(), g,
                                          g + 4 * self.n_vec, L, d, int(CFG["use_sigmoid"]), st),
                   "icv_scale_bwd")
-        if self.world > 1 and allreduce:
+        if self.world > 1:
             # logged scalars ride in the tail of the same flat buffer (one exchange per step)
             self.grad[self.n_vec + self.n_alpha:self.n_vec + self.n_alpha + 3].copy_(self.losses[:3])
-            if self.peer is not None:
-                self.step_no += 1
-                self._chk(lib.licv_dp_allreduce_adamw(
-                    self.peer.comm, p, g, self.m.data_ptr(), self.v.data_ptr(), self.n_vec,
-                    self.n_alpha, 4, 1e-4, 1e-2, 0.9, 0.999, 1e-8, 1e-3, self.step_no, 1.0,
-                    self.norm.data_ptr(), self.opt_ws.data_ptr(), st), "dp_allreduce_adamw")
-                return
-            torch.distributed.all_reduce(self.grad)
+
+    def optimize(self):
+        """(N > 1: exchange of the flat gradient, fused with) clip + AdamW."""
+        lib, st = self.lib, torch.cuda.current_stream().cuda_stream
+        p, g = self.param.data_ptr(), self.grad.data_ptr()
         self.step_no += 1
+        if self.world > 1 and self.peer is not None:
+            self._chk(lib.licv_dp_allreduce_adamw(
+                self.peer.comm, p, g, self.m.data_ptr(), self.v.data_ptr(), self.n_vec,
+                self.n_alpha, 4, 1e-4, 1e-2, 0.9, 0.999, 1e-8, 1e-3, self.step_no, 1.0,
+                self.norm.data_ptr(), self.opt_ws.data_ptr(), st), "dp_allreduce_adamw")
+            return
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grad)
         self._chk(lib.licv_adamw_step(p, g, self.m.data_ptr(), self.v.data_ptr(), self.n_vec,
                                       self.n_alpha, 1e-4, 1e-2, 0.9, 0.999, 1e-8, 1e-3,
                                       self.step_no, 1.0 / self.world, 1.0, self.norm.data_ptr(),
                                       self.opt_ws.data_ptr(), st), "adamw_step")
+
+    def step(self, batch):
+        self.compute(batch)
+        self.optimize()
 
 
 def time_kernel_launches(fn_list, stream):
@@ -313,37 +330,65 @@ def esize(dtype):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's eager op chain on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_steps(n_steps, warmup, seed=0):
-    from oracle import torch_chain
-    torch.set_num_threads(os.cpu_count() or 1)
-    # bf16 on the CPU where the GPU recipe is fp16: fp16 eager kernels on CPU are not what any
-    # user of the reference would run, bf16 is (lmm_base.yaml precision "bf16")
-    dt = torch.bfloat16
-    batch = make_batch("cpu", seed, dt)
+def reference_chain_inputs(device, seed=0):
+    """The batch of one step in the reference's own recipe - DeepSpeed "16-mixed": hidden states,
+    incoming gradients, logits AND the ICV parameters in fp16 (README.md:126-190, zero2.yaml) -
+    i.e. exactly the dtypes the B200 arm moves (2-byte h / g / out / dh / logits)."""
+    from oracle import torch_chain  # noqa: F401  (the chain itself; imported by the callers)
+    dt = torch.float16
+    batch = make_batch(device, seed, dt)
     L, d, V = CFG["layers"], CFG["d"], CFG["vocab"]
     B, T = CFG["batch_per_gpu"], CFG["student_tokens"]
-    alpha = torch.full((1, L), CFG["alpha_init_value"])
+    alpha = torch.full((1, L), CFG["alpha_init_value"]).to(dt).to(device)
     gen = torch.Generator().manual_seed(426)
-    vec = torch.randn(1, L, d, generator=gen) * 0.01
+    vec = (torch.randn(1, L, d, generator=gen) * 0.01).to(dt).to(device)
     hs = [h.view(B, T, d) for h in batch["h"]]
-    gs = [g.view(B, T, d).float() for g in batch["g"]]   # fp32 ICV -> fp32 result -> fp32 grad
-    stu_mask = torch.zeros(B, T, dtype=torch.bool)
+    gs = [g.view(B, T, d) for g in batch["g"]]
+    stu_mask = torch.zeros(B, T, dtype=torch.bool, device=device)
     stu_mask[:, T - CFG["kl_rows_per_sample"]:] = True
-    temp = torch.tensor(CFG["temperature"])
+    temp = torch.tensor(CFG["temperature"], device=device)
+    return dict(hs=hs, gs=gs, alpha=alpha, vec=vec, stu=batch["stu"].view(B, T, V), tea=batch["tea"],
+                stu_mask=stu_mask, ids=batch["ids"], att=batch["att"], temp=temp)
 
-    def one():
-        return torch_chain.hot_path_step(hs, gs, alpha, vec, CFG["use_sigmoid"],
-                                         batch["stu"].view(B, T, V), batch["tea"], stu_mask,
-                                         batch["ids"], batch["att"], temp, CFG["kl_eps"],
-                                         CFG["hard_loss_weight"])
 
+def reference_chain_step(x):
+    from oracle import torch_chain
+    return torch_chain.hot_path_step(x["hs"], x["gs"], x["alpha"], x["vec"], CFG["use_sigmoid"],
+                                     x["stu"], x["tea"], x["stu_mask"], x["ids"], x["att"], x["temp"],
+                                     CFG["kl_eps"], CFG["hard_loss_weight"])
+
+
+REFERENCE_RECIPE = ("oracle/torch_chain.py: the reference's eager op chain + autograd (icv_intervention.py:"
+                    "61-86, icv_module.py:89-134, HF shifted CE), fp16 hidden states / gradients / logits / "
+                    "ICV parameters like the B200 arm (DeepSpeed 16-mixed)")
+
+
+def cpu_reference_steps(n_steps, warmup, seed=0):
+    torch.set_num_threads(os.cpu_count() or 1)
+    x = reference_chain_inputs("cpu", seed)
     for _ in range(warmup):
-        one()
+        reference_chain_step(x)
     t0 = time.perf_counter()
     for _ in range(n_steps):
-        one()
+        reference_chain_step(x)
     dt_s = (time.perf_counter() - t0) / max(n_steps, 1)
     return dt_s, torch.get_num_threads()
+
+
+def eager_cuda_steps(device, n_steps=10, warmup=3):
+    """The same eager chain on the same B200 (stock PyTorch kernels): SURVEY 8(d)'s "real
+    comparator".  -> seconds per step, CUDA events on the current stream."""
+    x = reference_chain_inputs(device, 0)
+    for _ in range(warmup):
+        reference_chain_step(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_steps):
+        reference_chain_step(x)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / n_steps
 
 
 def run_reference(args):
@@ -357,13 +402,13 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 activations / fp32 ICV (CPU eager)",
-        "data": "synthetic", "config": dict(CFG, flush="inputs of one step (~290 MB) exceed L2"),
+        "scaling": "weak", "vs_baseline": None, "dtype": CFG["dtype"] + " (fp32 accumulate)",
+        "data": "synthetic", "config": config_of(args.gpus),
+        "arm": {"recipe": REFERENCE_RECIPE, "where": "host CPU, rank 0 only (one process, one "
+                "8-sample batch per step; world-size independent)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{steps} full steps of the same workload (one 8-sample batch "
-                                   "each; rank 0 only, world-size independent) through "
-                                   "oracle/torch_chain.py, the reference's eager op chain + "
-                                   "autograd on the host CPU"},
+                                   "each) through " + REFERENCE_RECIPE},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -372,73 +417,222 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# correctness evidence for the JSON line
+# ------------------------------------------------------------------------------------------------
+def dp_check(hp, batch):
+    """One warm-up step at N > 1, twice: through the exchange this run uses, and - on copies of the
+    same state - through torch.distributed.all_reduce + licv_adamw_step.  Also: every replica holds
+    bit-identical parameters afterwards, and no wait for a peer timed out."""
+    dist = torch.distributed
+    hp.compute(batch)
+    torch.cuda.synchronize()
+    n = hp.n_vec + hp.n_alpha
+    p2, g2, m2, v2 = hp.param.clone(), hp.grad.clone(), hp.m.clone(), hp.v.clone()
+    norm2, ws2 = torch.zeros(1, device=hp.device), torch.zeros(16, dtype=torch.uint8, device=hp.device)
+    hp.optimize()
+    dist.all_reduce(g2)
+    hp._chk(hp.lib.licv_adamw_step(p2.data_ptr(), g2.data_ptr(), m2.data_ptr(), v2.data_ptr(), hp.n_vec,
+                                   hp.n_alpha, 1e-4, 1e-2, 0.9, 0.999, 1e-8, 1e-3, hp.step_no,
+                                   1.0 / hp.world, 1.0, norm2.data_ptr(), ws2.data_ptr(),
+                                   torch.cuda.current_stream().cuda_stream), "adamw_step (check)")
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+    bits = hp.param.view(torch.int32).to(torch.int64)
+    chk = torch.stack([bits.sum(), (bits * torch.arange(1, bits.numel() + 1, device=hp.device)).sum()])
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    out = {"exchange_vs_nccl_grad_rel_err": rel(hp.grad[:n + 3], g2[:n + 3]),
+           "exchange_vs_nccl_param_rel_err": rel(hp.param, p2),
+           "exchange_vs_nccl_grad_norm_rel_err": rel(hp.norm, norm2),
+           "replicas_bit_identical": bool(torch.equal(lo, hi)),
+           "comm_error": (int(hp.peer.timed_out()) if hp.peer is not None else 0)}
+    t = torch.tensor([out["exchange_vs_nccl_grad_rel_err"], out["exchange_vs_nccl_param_rel_err"],
+                      out["exchange_vs_nccl_grad_norm_rel_err"], float(out["comm_error"])], device=hp.device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)      # worst rank
+    out["exchange_vs_nccl_grad_rel_err"], out["exchange_vs_nccl_param_rel_err"] = float(t[0]), float(t[1])
+    out["exchange_vs_nccl_grad_norm_rel_err"], out["comm_error"] = float(t[2]), int(t[3])
+    return out
+
+
+def oracle_check(hp, batch):
+    """The timed step's arithmetic against the float64 oracle (oracle/licv_oracle.py, the checker
+    that tests/ pins to the reference's golden vectors) on the same batch: losses, d_icv of every
+    layer, d_vec / d_alpha, sampled rows of d(logits).  CPU, outside every timed region."""
+    import numpy as np
+    from oracle import licv_oracle as O
+    L, d, V = CFG["layers"], CFG["d"], CFG["vocab"]
+    B, T, K4 = CFG["batch_per_gpu"], CFG["student_tokens"], CFG["kl_rows_per_sample"]
+    hp.compute(batch)
+    torch.cuda.synchronize()
+
+    def host(t):
+        return t.detach().float().cpu().numpy().astype(np.float64)
+
+    def rel(a, b):
+        den = np.linalg.norm(np.asarray(b).ravel())
+        return float(np.linalg.norm((np.asarray(a) - np.asarray(b)).ravel()) / (den if den > 0 else 1.0))
+
+    icv = host(hp.icv)
+    worst_ds, worst_dh = 0.0, 0.0
+    for l in range(L):
+        o_dh, o_ds = O.inject_bwd(host(batch["h"][l]), icv[l], host(batch["g"][l]), hp.flags, CFG["dtype"])
+        worst_ds = max(worst_ds, rel(host(hp.sink[l]), o_ds))
+        if l in (0, L - 1):
+            worst_dh = max(worst_dh, rel(host(hp.dh[l]), o_dh))
+    alpha = host(hp.param[hp.n_vec:hp.n_vec + hp.n_alpha])
+    vec = host(hp.param[:hp.n_vec]).reshape(L, d)
+    sink = host(hp.sink)
+    d_vec_o, d_alpha_o = alpha[:, None] * sink, (sink * vec).sum(1)
+    ktr = np.full(B * T, -1, np.int32)
+    lab = np.full(B * T, -100, np.int64)
+    ids = batch["ids"].cpu().numpy()
+    for b in range(B):
+        for k in range(K4):
+            ktr[b * T + T - K4 + k] = b * K4 + k
+        lab[b * T:b * T + T - 1] = ids[b, 1:]
+    want = O.kd_loss_rows(host(batch["stu"]), host(batch["tea"]), ktr, lab, CFG["temperature"],
+                          CFG["kl_eps"], CFG["hard_loss_weight"], logit_fmt=CFG["dtype"])
+    got = [float(x) for x in hp.losses[:3].cpu()]
+    rows = [0, T - 2, T - 1, B * T - 3, B * T - 1]
+    return {"loss_rel_err": abs(got[2] - want["loss"]) / abs(want["loss"]),
+            "kl_rel_err": abs(got[0] - want["kl"]) / abs(want["kl"]),
+            "ce_rel_err": abs(got[1] - want["ce"]) / abs(want["ce"]),
+            "d_icv_rel_err_worst_layer": worst_ds, "dh_rel_err": worst_dh,
+            "d_vec_rel_err": rel(host(hp.grad[:hp.n_vec]).reshape(L, d), d_vec_o),
+            "d_alpha_rel_err": rel(host(hp.grad[hp.n_vec:hp.n_vec + hp.n_alpha]), d_alpha_o),
+            "dstu_rows_rel_err": rel(host(hp.dstu[rows]), want["d_stu"][rows]),
+            "against": "oracle/licv_oracle.py (float64, same fp16 inputs and rounding points); "
+                       "tolerances of tests/: losses 1e-5, d_icv / d_vec / d_alpha 1e-4, dh and "
+                       "d(logits) the fp16 roundoff 6e-4"}
+
+
+# ------------------------------------------------------------------------------------------------
 # main arm
 # ------------------------------------------------------------------------------------------------
 def bandwidth_shapes(hp, peak):
-    """configs[4]-sized launches of the same kernels: bandwidth-bound roofline points."""
+    """configs[4]-sized launches of the same kernels: bandwidth-bound roofline points.
+
+    Every shape is measured on TWO freshly allocated buffer sets (torch.cuda.empty_cache() first)
+    and the faster one is reported, all samples listed: on this pool a buffer set occasionally
+    lands on memory where EVERY kernel - torch's own copy included - runs 2-4x slower for the
+    lifetime of the allocation (profiles/README.md, r2q); that is a property of the placement,
+    not of the kernel."""
     lib, st = hp.lib, torch.cuda.current_stream().cuda_stream
     out = []
     d, V = CFG["d"], CFG["vocab"]
     dt, code, es = hp.dtype, hp.code, esize(hp.dtype)
     n_tok = 64 * 2048                                   # bs 64 x T 2048, 1 GiB in
-    h = [(torch.randn(n_tok, d, device=hp.device) * 4).to(dt) for _ in range(2)]
-    g = [torch.randn(n_tok, d, device=hp.device).to(dt) for _ in range(2)]
-    o = torch.empty(n_tok, d, dtype=dt, device=hp.device)
+
+    def measure(name, shape, nbytes, make, launch, n_launch, n_warm):
+        samples = []
+        for _ in range(2):
+            torch.cuda.empty_cache()
+            bufs = make()
+            for i in range(n_warm):
+                launch(bufs, i)
+            ts = time_kernel_launches([lambda i=i: launch(bufs, i) for i in range(n_launch)],
+                                      torch.cuda.current_stream())
+            samples.append(sum(ts) / len(ts))
+            del bufs
+        t = min(samples)
+        out.append({"kernel": name, "shape": shape, "achieved": nbytes / t / 1e9, "peak": peak,
+                    "unit": "GB/s", "frac": nbytes / t / 1e9 / peak,
+                    "frac_of_nominal_8tbs": nbytes / t / 8e12, "us": t * 1e6,
+                    "us_per_allocation": [round(x * 1e6, 1) for x in samples]})
+
     s = hp.icv[0]
     ds = torch.zeros(d, device=hp.device)
-    for name, nbytes, fn in [
-        ("licv_inject_fwd", 2 * es * n_tok * d,
-         lambda i: lib.licv_inject_fwd(h[i % 2].data_ptr(), s.data_ptr(), o.data_ptr(), n_tok, d,
-                                       code, code, hp.flags, st)),
-        ("licv_inject_bwd", 3 * es * n_tok * d,
-         lambda i: lib.licv_inject_bwd(h[i % 2].data_ptr(), g[i % 2].data_ptr(), s.data_ptr(),
-                                       o.data_ptr(), ds.data_ptr(), n_tok, d, code, code, hp.flags,
-                                       st)),
-    ]:
-        for i in range(3):
-            fn(i)
-        ts = time_kernel_launches([lambda i=i: fn(i) for i in range(6)], torch.cuda.current_stream())
-        t = sum(ts) / len(ts)
-        out.append({"kernel": name, "shape": f"n_tok={n_tok} d={d} {CFG['dtype']}",
-                    "achieved": nbytes / t / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": nbytes / t / 1e9 / peak, "frac_of_nominal_8tbs": nbytes / t / 8e12,
-                    "us": t * 1e6})
-    del h, g, o
+
+    def make_inject():
+        return ([(torch.randn(n_tok, d, device=hp.device) * 4).to(dt) for _ in range(2)],
+                [torch.randn(n_tok, d, device=hp.device).to(dt) for _ in range(2)],
+                torch.empty(n_tok, d, dtype=dt, device=hp.device))
+
+    measure("licv_inject_fwd", f"n_tok={n_tok} d={d} {CFG['dtype']}", 2 * es * n_tok * d, make_inject,
+            lambda b, i: lib.licv_inject_fwd(b[0][i % 2].data_ptr(), s.data_ptr(), b[2].data_ptr(), n_tok,
+                                             d, code, code, hp.flags, st), 6, 3)
+    measure("licv_inject_bwd", f"n_tok={n_tok} d={d} {CFG['dtype']}", 3 * es * n_tok * d, make_inject,
+            lambda b, i: lib.licv_inject_bwd(b[0][i % 2].data_ptr(), b[1][i % 2].data_ptr(), s.data_ptr(),
+                                             b[2].data_ptr(), ds.data_ptr(), n_tok, d, code, code,
+                                             hp.flags, st), 6, 3)
     R = 8192
-    stu = [(torch.randn(R, V, device=hp.device) * 3).to(dt) for _ in range(2)]
-    tea = [(torch.randn(R, V, device=hp.device) * 3).to(dt) for _ in range(2)]
-    dst = torch.empty(R, V, dtype=dt, device=hp.device)
     lab = torch.randint(0, V, (R,), device=hp.device)
     ws = torch.zeros(lib.licv_kd_loss_workspace_bytes(R) + 64, dtype=torch.uint8, device=hp.device)
     losses = torch.zeros(4, device=hp.device)
 
-    def kd(i):
-        lib.licv_kd_loss_fwd_bwd(stu[i % 2].data_ptr(), dst.data_ptr(), tea[i % 2].data_ptr(), 0,
+    def make_kd():
+        return ([(torch.randn(R, V, device=hp.device) * 3).to(dt) for _ in range(2)],
+                [(torch.randn(R, V, device=hp.device) * 3).to(dt) for _ in range(2)],
+                torch.empty(R, V, dtype=dt, device=hp.device))
+
+    def kd(b, i):
+        lib.licv_kd_loss_fwd_bwd(b[0][i % 2].data_ptr(), b[2].data_ptr(), b[1][i % 2].data_ptr(), 0,
                                  lab.data_ptr(), 0, R, R, 1.0, 1e-6, 0.5, 0, 1.0,
                                  losses.data_ptr(), ws.data_ptr(), R, V, V, V, code, 16, st)
 
-    def kd_ce(i):      # only_hard_loss: every row is a CE row, no teacher
-        lib.licv_kd_loss_fwd_bwd(stu[i % 2].data_ptr(), dst.data_ptr(), 0, 0, lab.data_ptr(), 0, 0, R,
+    def kd_ce(b, i):      # only_hard_loss: every row is a CE row, no teacher
+        lib.licv_kd_loss_fwd_bwd(b[0][i % 2].data_ptr(), b[2].data_ptr(), 0, 0, lab.data_ptr(), 0, 0, R,
                                  1.0, 1e-6, 0.5, 1, 1.0, losses.data_ptr(), ws.data_ptr(), R, V, V,
                                  V, code, 16, st)
 
-    for fn, what, per_row in ((kd, "KL+CE rows", 3), (kd_ce, "CE-only rows", 2)):
-        for i in range(2):
-            fn(i)
-        ts = time_kernel_launches([lambda i=i, fn=fn: fn(i) for i in range(4)],
-                                  torch.cuda.current_stream())
-        t = sum(ts) / len(ts)
-        nbytes = per_row * es * R * V
-        out.append({"kernel": "licv_kd_loss_fwd_bwd", "shape": f"R={R} {what} V={V} {CFG['dtype']}",
-                    "achieved": nbytes / t / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": nbytes / t / 1e9 / peak, "frac_of_nominal_8tbs": nbytes / t / 8e12,
-                    "us": t * 1e6})
+    measure("licv_kd_loss_fwd_bwd", f"R={R} KL+CE rows V={V} {CFG['dtype']}", 3 * es * R * V, make_kd, kd, 4, 2)
+    measure("licv_kd_loss_fwd_bwd", f"R={R} CE-only rows V={V} {CFG['dtype']}", 2 * es * R * V, make_kd,
+            kd_ce, 4, 2)
+    torch.cuda.empty_cache()
     return out
 
 
+def bind_near_gpu(index):
+    """Best effort: run this process, and place the pinned buffers it allocates, on the NUMA node
+    the GPU hangs off (eight ranks that all pin on node 0 share one socket's memory and the
+    inter-socket link).  -> what was done, for the JSON line."""
+    note = {}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        note["gpu_numa_node"] = node
+        if node < 0:
+            return note
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use:
+            os.sched_setaffinity(0, use)
+            note["cpu_affinity"] = f"{len(use)} cpus of node {node}"
+        else:
+            note["cpu_affinity"] = f"node {node} cpus not in this container's cpuset ({len(allowed)} allowed)"
+        # memory policy: prefer that node for what this thread allocates from here on
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))   # set_mempolicy(MPOL_PREFERRED)
+        note["mempolicy"] = "preferred node %d" % node if rc == 0 else "set_mempolicy errno %d" % ctypes.get_errno()
+    except Exception as exc:      # not fatal: the measurement simply runs where the process is
+        note["error"] = repr(exc)[:120]
+    return note
+
+
 def run_e2e_host(hp, steps, warmup, seed):
-    """The step through the host-buffer entry points: inputs in pinned host memory, results back
-    in pinned host memory, all copies inside the timed region."""
+    """The SAME step through the host-buffer entry points: every tensor of the step starts in
+    pinned host memory and every result ends there - hidden states, gradients, logits through
+    licv_*_host; the ICV product, the row lists, d_vec / d_alpha and the clip + AdamW update on
+    131 104 floats are host-side work of a host plugin and run inside the timed region too."""
     import ctypes as C
     lib = hp.lib
     L, d, V = CFG["layers"], CFG["d"], CFG["vocab"]
@@ -450,25 +644,37 @@ def run_e2e_host(hp, steps, warmup, seed):
     dstu_h = torch.empty(n_tok, V, dtype=hp.dtype).pin_memory()
     ds_h = torch.zeros(L, d).pin_memory()
     loss_h = torch.zeros(4).pin_memory()
-    icv_h = (hp.param[:L * d].view(L, d) * CFG["alpha_init_value"]).cpu().pin_memory()
-    # row lists are host-side integer work for a host plugin
+    icv_h = torch.empty(L, d).pin_memory()
     T4 = CFG["kl_rows_per_sample"]
-    ktr = torch.full((n_tok,), -1, dtype=torch.int32)
-    lab = torch.full((n_tok,), -100, dtype=torch.int64)
+    ktr = torch.empty(n_tok, dtype=torch.int32).pin_memory()
+    lab = torch.empty(n_tok, dtype=torch.int64).pin_memory()
     ids = hb["ids"]
-    for b in range(B):
-        for k in range(T4):
-            ktr[b * T + T - T4 + k] = b * T4 + k
-        lab[b * T:b * T + T - 1] = ids[b, 1:]
-    ktr, lab = ktr.pin_memory(), lab.pin_memory()
-    n_kl, n_ce = int((ktr >= 0).sum()), int((lab != -100).sum())
+    # host-resident parameters and optimizer state
+    alpha = torch.full((L,), CFG["alpha_init_value"])
+    vec = hp.param[:L * d].view(L, d).cpu().clone()
+    m_v, v_v, m_a, v_a = torch.zeros(L, d), torch.zeros(L, d), torch.zeros(L), torch.zeros(L)
+    step_no = [0]
     sess = C.c_void_p()
     scratch = max(3 * n_tok * d * es + 4 * d * 4 + 4096,
                   (n_tok + B * T4) * V * es + n_tok * 16 + 65536) + (1 << 20)
     n_slots = env_int("LICV_E2E_SLOTS", 16)
     hp.abi.check(lib.licv_host_session_create(C.byref(sess), scratch, n_slots), "host_session_create")
 
+    def adamw(p, g, m, v, lr, coef, t):
+        g = g * coef
+        p.mul_(1.0 - lr * 1e-3)
+        m.mul_(0.9).add_(g, alpha=0.1)
+        v.mul_(0.999).addcmul_(g, g, value=0.001)
+        p.addcdiv_(m, (v.sqrt() / (1.0 - 0.999 ** t) ** 0.5).add_(1e-8), value=-lr / (1.0 - 0.9 ** t))
+
     def step():
+        # a1 + a2: the product that crosses into the hooks; a6 + a7 + a9: row pairing and labels
+        torch.mul(alpha.unsqueeze(-1), vec, out=icv_h)
+        ktr.fill_(-1)
+        ktr.view(B, T)[:, T - T4:] = (torch.arange(B).unsqueeze(1) * T4 + torch.arange(T4)).to(torch.int32)
+        lab.fill_(-100)
+        lab.view(B, T)[:, :T - 1] = ids[:, 1:]
+        n_kl, n_ce = B * T4, B * (T - 1)
         for l in range(L):
             # the forward keeps h on the device for its backward (saved-for-backward), so the
             # backward moves only g in and dh out
@@ -486,6 +692,14 @@ def run_e2e_host(hp, steps, warmup, seed):
                                                         ds_h[l].data_ptr(), n_tok, d, hp.code,
                                                         hp.code, hp.flags), "inject_bwd_host_saved")
         hp.abi.check(lib.licv_host_sync(sess), "host_sync")
+        # autograd of a2, then f2: global-norm clip + AdamW with the two learning rates
+        d_vec = alpha.unsqueeze(-1) * ds_h
+        d_alpha = (ds_h * vec).sum(1)
+        norm = float((d_vec.square().sum() + d_alpha.square().sum()).sqrt())
+        coef = min(1.0, 1.0 / (norm + 1e-6))
+        step_no[0] += 1
+        adamw(vec, d_vec, m_v, v_v, 1e-4, coef, step_no[0])
+        adamw(alpha, d_alpha, m_a, v_a, 1e-2, coef, step_no[0])
         return float(loss_h[2])   # the device->host read of the step's result
 
     for _ in range(warmup):
@@ -505,17 +719,19 @@ def run_e2e_host(hp, steps, warmup, seed):
 def e2e_child(args):
     """The e2e leg in its own process (its own CUDA context): a stall there cannot take the main
     measurement down with it."""
+    numa = bind_near_gpu(args.e2e_child)      # before anything is pinned
+    torch.set_num_threads(max(1, min(8, len(os.sched_getaffinity(0)))))
     torch.cuda.set_device(args.e2e_child)
     device = torch.device("cuda", args.e2e_child)
     dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[CFG["dtype"]]
     hp = HotPath(device, dtype, 1)
     sec, h2d, d2h = run_e2e_host(hp, args.steps, args.warmup, 1000 + env_int("RANK", 0))
-    print(json.dumps({"e2e_child": True, "sec": sec, "h2d": h2d, "d2h": d2h}), flush=True)
+    print(json.dumps({"e2e_child": True, "sec": sec, "h2d": h2d, "d2h": d2h, "numa": numa}), flush=True)
     return 0
 
 
 def run_e2e_subprocess(device_index, steps, warmup, timeout_s=240):
-    """-> (sec, h2d, d2h, path) or raises.  Tries the zero-copy host path, then the staged one."""
+    """-> (sec, h2d, d2h, path, numa note) or raises.  Tries the zero-copy host path, then the staged one."""
     import subprocess
     last = None
     for zero_copy in ("1", "0"):
@@ -530,7 +746,8 @@ def run_e2e_subprocess(device_index, steps, warmup, timeout_s=240):
             for ln in out.stdout.splitlines():
                 if ln.startswith("{") and "e2e_child" in ln:
                     r = json.loads(ln)
-                    return r["sec"], r["h2d"], r["d2h"], ("zero-copy" if zero_copy == "1" else "staged")
+                    return (r["sec"], r["h2d"], r["d2h"], ("zero-copy" if zero_copy == "1" else "staged"),
+                            r.get("numa", {}))
             last = f"rc={out.returncode}: {out.stderr[-300:]}"
         except subprocess.TimeoutExpired:
             last = f"timed out after {timeout_s}s"
@@ -573,9 +790,18 @@ def main():
 
     stream = torch.cuda.Stream()
     graph = None
+    checks = {}
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
             hp.step(batch)
+        stream.synchronize()
+        # correctness evidence, outside every timed region: the exchange against NCCL + the same
+        # optimizer kernel on copies (N > 1), the step's arithmetic against the float64 oracle
+        if world > 1:
+            checks.update(dp_check(hp, batch))
+        if rank == 0 and not args.no_extras:
+            checks.update(oracle_check(hp, batch))
+        hp.step(batch)          # every rank back in the same state of the step sequence
         stream.synchronize()
         if not args.no_graph:
             graph = torch.cuda.CUDAGraph()
@@ -590,22 +816,33 @@ def main():
                 torch.distributed.barrier()
             torch.cuda.synchronize()
 
+        def one_step():
+            if graph is not None:
+                graph.replay()
+            else:
+                hp.step(batch)
+
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        clocks = ClockSampler(local)     # NVML set-up BEFORE the barrier: it takes milliseconds
         barrier()
-        with ClockSampler(local) as clocks:
+        for _ in range(2):               # untimed: the first exchange after a barrier aligns the ranks
+            one_step()
+        with clocks:
             e0.record(stream)
-            for _ in range(args.steps):
-                if graph is not None:
-                    graph.replay()
-                else:
-                    hp.step(batch)
+            for k in range(args.steps):
+                one_step()
+                marks[k].record(stream)
             e1.record(stream)
             barrier()
         sec = e0.elapsed_time(e1) * 1e-3
+        per_step = sorted(((marks[k - 1] if k else e0).elapsed_time(marks[k]) for k in range(args.steps)))
+        step_stats = [per_step[len(per_step) // 2], per_step[min(len(per_step) - 1, int(0.9 * len(per_step)))],
+                      per_step[-1]]
         if world > 1:
-            t = torch.tensor([sec], device=device)
+            t = torch.tensor([sec] + step_stats, device=device)
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            sec = float(t)
+            sec, step_stats = float(t[0]), [float(x) for x in t[1:]]
         ms_per_step = sec / args.steps * 1e3
         value = CFG["batch_per_gpu"] * world / (sec / args.steps)
 
@@ -692,16 +929,18 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": CFG["dtype"] + " (fp32 accumulate)",
-        "data": "synthetic",
-        "config": dict(CFG, global_batch=CFG["batch_per_gpu"] * world, parallelism=f"dp{world}",
-                       grad_exchange=("none (1 GPU)" if world == 1 else
-                                      "fused p2p exchange + AdamW over NVLink peer memory"
-                                      if hp.peer is not None else "nccl all_reduce" + hp.peer_note),
-                       cuda_graph=graph is not None,
-                       flush="inputs of one step (~290 MB, a distinct buffer per layer) exceed L2"),
+        "data": "synthetic", "config": config_of(world),
+        "arm": {"grad_exchange": ("none (1 GPU)" if world == 1 else
+                                  "fused p2p exchange + AdamW over NVLink peer memory"
+                                  if hp.peer is not None else "nccl all_reduce" + hp.peer_note),
+                "cuda_graph": graph is not None, "gpu": torch.cuda.get_device_name(local)},
+        "step_ms": {"median": step_stats[0], "p90": step_stats[1], "max": step_stats[2],
+                    "how": "CUDA event after every step of the timed region; max over ranks"},
         "roofline": roofline, "clocks": clocks.summary(),
         "gpu_launches": (HotPath.LAUNCHES_PER_STEP) * args.steps,
     }
+    if checks:
+        line["checks"] = checks
 
     if rank == 0 and not args.no_extras:
         with torch.cuda.stream(stream):
@@ -710,31 +949,48 @@ def main():
     if not args.no_extras:
         e_steps = max(3, min(args.steps, 20))
         try:
-            e_sec, h2d, d2h, e_path = run_e2e_subprocess(local, e_steps, 3)
+            e_sec, h2d, d2h, e_path, numa = run_e2e_subprocess(local, e_steps, 3)
         except RuntimeError as exc:
-            e_sec, h2d, d2h, e_path = float("nan"), 0, 0, str(exc)
+            e_sec, h2d, d2h, e_path, numa = float("nan"), 0, 0, str(exc), {}
+        e_mine = e_sec
         if world > 1:
             t = torch.tensor([e_sec], device=device)
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
             e_sec = float(t)
+            per_rank = [torch.zeros(1, device=device) for _ in range(world)]
+            torch.distributed.all_gather(per_rank, torch.tensor([e_mine], device=device))
+            per_rank = [float(x) for x in per_rank]
+        else:
+            per_rank = [e_mine]
         ok = e_sec == e_sec
         line["e2e"] = {"value": CFG["batch_per_gpu"] * world / e_sec if ok else None, "unit": UNIT,
                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": e_sec * 1e3 if ok else None, "steps": e_steps, "path": e_path,
-                       "how": "licv_*_host entry points on one pipelined session (own process): "
-                              "every input starts in pinned host memory and every result ends "
-                              "there, inside the timed region; zero-copy = the kernels read and "
-                              "write the pinned host buffers over PCIe themselves, staged = "
-                              "cudaMemcpyAsync through device scratch"}
+                       "per_rank_ms": [round(x * 1e3, 3) for x in per_rank],
+                       "per_rank_link_gbs_each_way": [round((h2d + d2h) / 2 / x / 1e9, 1) if x == x and x > 0
+                                                      else None for x in per_rank],
+                       "numa": numa,
+                       "how": "the same step through the licv_*_host entry points on one pipelined "
+                              "session (own process, bound to the GPU's NUMA node where the "
+                              "container allows): hidden states, gradients and logits start in pinned "
+                              "host memory and end there, the ICV product, row lists, d_vec / d_alpha "
+                              "and clip + AdamW are host-side work inside the timed region; zero-copy "
+                              "= the kernels read and write the pinned host buffers over PCIe "
+                              "themselves, staged = cudaMemcpyAsync through device scratch"}
     if rank == 0 and world == 1 and not args.no_extras:
         one, cores = cpu_reference_steps(1, 1)
         n = max(2, min(40, int(12.0 / max(one, 1e-3))))
         sec_cpu, cores = cpu_reference_steps(n, 0)
         line["cpu_baseline"] = {"value": CFG["batch_per_gpu"] / sec_cpu, "unit": UNIT,
                                 "cores": cores, "kind": "port", "ms_per_step": sec_cpu * 1e3,
-                                "sample": f"{n} full steps of the same workload through "
-                                          "oracle/torch_chain.py (the reference's eager op chain "
-                                          "+ autograd, bf16 activations, fp32 ICV) on the host CPU"}
+                                "sample": f"{n} full steps of the same workload through " + REFERENCE_RECIPE}
+        with torch.cuda.stream(stream):
+            sec_eager = eager_cuda_steps(device)
+        line["eager_cuda_baseline"] = {
+            "value": CFG["batch_per_gpu"] / sec_eager, "unit": UNIT, "ms_per_step": sec_eager * 1e3,
+            "what": "the same eager chain (oracle/torch_chain.py) in stock PyTorch on this B200, inputs "
+                    "resident, CUDA events around 10 steps - SURVEY 8(d)'s same-box comparator",
+            "speedup_of_value": value / (CFG["batch_per_gpu"] / sec_eager)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -720,7 +720,10 @@ def e2e_child(args):
     """The e2e leg in its own process (its own CUDA context): a stall there cannot take the main
     measurement down with it."""
     numa = bind_near_gpu(args.e2e_child)      # before anything is pinned
-    torch.set_num_threads(max(1, min(8, len(os.sched_getaffinity(0)))))
+    # the host-side part of the step is a few vector operations on 131 104 floats: a handful of
+    # threads, and never more than this rank's share of the host's cores
+    share = len(os.sched_getaffinity(0)) // max(1, env_int("LICV_E2E_WORLD", 1))
+    torch.set_num_threads(max(1, min(4, share)))
     torch.cuda.set_device(args.e2e_child)
     device = torch.device("cuda", args.e2e_child)
     dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[CFG["dtype"]]
@@ -735,7 +738,8 @@ def run_e2e_subprocess(device_index, steps, warmup, timeout_s=240):
     import subprocess
     last = None
     for zero_copy in ("1", "0"):
-        env = dict(os.environ, LICV_HOST_ZERO_COPY=zero_copy)
+        env = dict(os.environ, LICV_HOST_ZERO_COPY=zero_copy,
+                   LICV_E2E_WORLD=os.environ.get("WORLD_SIZE", "1"))
         for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
             if k != "RANK":
                 env.pop(k, None)

@@ -209,6 +209,19 @@ int licv_kd_loss_fwd_bwd(const void* stu, void* dstu, const void* tea, const int
                          int only_hard_loss, float grad_scale, float* out_losses, void* workspace,
                          int64_t n_rows, int vocab, int64_t stu_stride, int64_t tea_stride,
                          int dtype, unsigned round_flags, licv_stream_t stream);
+/* The same with a learnable temperature (learnable_t, icv_src/icv_module.py:49-52): out_losses4
+ * [4] = {kl_loss, ce_loss, loss, d loss / d temperature} - both in-place divides by T
+ * (icv_module.py:122-123) and the T^2 factor (:133) are differentiated, like the reference's
+ * autograd does.  Runs the generic kernel (it re-reads the logits it needs);
+ * workspace: licv_kd_loss_dtemp_workspace_bytes(R). */
+int64_t licv_kd_loss_dtemp_workspace_bytes(int64_t n_rows);
+int licv_kd_loss_fwd_bwd_dtemp(const void* stu, void* dstu, const void* tea, const int32_t* kl_tea_row,
+                               const int64_t* ce_label, const int32_t* counts, int64_t n_kl,
+                               int64_t n_ce, float temperature, float kl_eps, float hard_loss_weight,
+                               int only_hard_loss, float grad_scale, float* out_losses4,
+                               void* workspace, int64_t n_rows, int vocab, int64_t stu_stride,
+                               int64_t tea_stride, int dtype, unsigned round_flags,
+                               licv_stream_t stream);
 
 /* x[i] *= *scale for i < n, skipped entirely (no traffic) when *scale == 1: the upstream
  * gradient of the loss applied to the in-place dstu in the autograd backward. */

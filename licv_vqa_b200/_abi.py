@@ -44,6 +44,9 @@ SIGNATURES = {
     "licv_debug_set_kd_stream": (None, [_i32]),
     "licv_kd_loss_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32,
                                     _i32, _f32, _vp, _vp, _i64, _i32, _i64, _i64, _i32, _u32, _vp]),
+    "licv_kd_loss_fwd_bwd_dtemp": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32,
+                                    _i32, _f32, _vp, _vp, _i64, _i32, _i64, _i64, _i32, _u32, _vp]),
+    "licv_kd_loss_dtemp_workspace_bytes": (_i64, [_i64]),
     "licv_scale_inplace": (_i32, [_vp, _i64, _vp, _i32, _vp]),
     "licv_adamw_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32,
                                _i64, _f32, _f32, _vp, _vp, _vp]),

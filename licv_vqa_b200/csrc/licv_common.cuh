@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <cstdlib>
+#include <mutex>
 
 #include "licv_b200.h"
 
@@ -169,6 +170,32 @@ struct DeviceInfo {
     int status = LICV_ERR_NO_DEVICE;
 };
 const DeviceInfo& device_info();
+
+// Launch constants that depend on the device (occupancy, "this function's shared-memory limit was
+// raised"): computed once PER DEVICE, thread-safely - the entry points are re-entrant, a process may
+// drive several GPUs, and autograd calls the backward ops from its own per-device threads.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return (d < 0 || d >= kMaxDevices) ? 0 : d;
+}
+template <typename T>
+class PerDevice {
+    T v_[kMaxDevices] = {};
+    std::once_flag once_[kMaxDevices];
+
+public:
+    template <typename F>
+    const T& get(F&& make) {
+        const int d = current_device();
+        std::call_once(once_[d], [&] { v_[d] = make(); });
+        return v_[d];
+    }
+};
 
 // Upper bound on the CTAs of the next injection launches of this thread (0 = none).  The
 // host-buffer entry points set it: when the operands live in host memory the link, not the SMs,

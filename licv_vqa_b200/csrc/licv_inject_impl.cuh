@@ -47,7 +47,8 @@ int launch_fwd(const Args& a0, const Launch& L) {
     auto kern = fwd_kernel<HDT, ODT, VPT, TB, RND>;
     const int groups = kCtaThreads / L.plan.gt > 0 ? kCtaThreads / L.plan.gt : 1;
     const int threads = groups * L.plan.gt;
-    static const int per_sm = resident_ctas_per_sm(kern, kCtaThreads, 0);
+    static PerDevice<int> per_sm_dev;
+    const int per_sm = per_sm_dev.get([&] { return resident_ctas_per_sm(kern, kCtaThreads, 0); });
     int64_t cap = (int64_t)per_sm * device_info().sm_count;
     if (tl_grid_cap > 0 && tl_grid_cap < cap) cap = tl_grid_cap;
     const int64_t need = ((L.n_tok + TB - 1) / TB + groups - 1) / groups;
@@ -72,13 +73,13 @@ int launch_bwd(const Args& a0, const Launch& L) {
     // one fp32 row (nvec * EPV floats) per extra group
     const size_t smem = (size_t)(groups - 1) * L.nvec * Fmt<HDT>::kPerVec * sizeof(float);
     if (smem > 48 * 1024) {
-        static bool raised = false;
-        if (!raised) {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            raised = true;
-        }
+        static PerDevice<int> raised;
+        raised.get([&] {
+            return (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        });
     }
-    static const int per_sm = resident_ctas_per_sm(kern, kCtaThreads, 16 * 1024);
+    static PerDevice<int> per_sm_dev;
+    const int per_sm = per_sm_dev.get([&] { return resident_ctas_per_sm(kern, kCtaThreads, 16 * 1024); });
     int64_t cap = (int64_t)per_sm * device_info().sm_count;
     if (tl_grid_cap > 0 && tl_grid_cap < cap) cap = tl_grid_cap;
     const int tok_per_group = TB > min_tok ? TB : min_tok;
@@ -136,12 +137,12 @@ int launch_bwd_pipe(const Args& a, const Launch& L) {
     if (stages > kPipeMaxStages) stages = kPipeMaxStages;
     if (stages < 2) return LICV_ERR_BAD_DIM;
     const size_t smem = (size_t)stages * kStage;
-    static size_t raised = 0;   // per instantiation; one process drives one GPU
-    if (smem > raised) {
-        const cudaError_t e = cudaFuncSetAttribute(
-            kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        raised = smem;
+    static PerDevice<int> raised;   // smem is a constant of the instantiation
+    {
+        const int e = raised.get([&] {
+            return (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        });
+        if (e != 0) return e;
     }
     PipeArgs pa;
     pa.a = a;
@@ -161,25 +162,23 @@ int launch_bwd_pipe(const Args& a, const Launch& L) {
     cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
     cfg.numAttrs = launch_attrs(attr, C > 1 ? C : 0);
-    // resident CTAs: whole clusters that fit the device at once
-    static int64_t cap = 0;
-    static size_t cap_smem = 0;
-    static int cap_c = 0;
-    if (cap == 0 || cap_smem != smem || cap_c != C) {
+    // resident CTAs: whole clusters that fit the device at once (per cluster size and device)
+    static PerDevice<int64_t> cap_by_c[9];
+    const int64_t cap = cap_by_c[C].get([&]() -> int64_t {
         int n_clusters = 0;
+        int64_t c;
         cfg.gridDim = dim3(C * device_info().sm_count);
         if (C > 1 && cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg) == cudaSuccess &&
             n_clusters > 0) {
-            cap = (int64_t)n_clusters * C;
+            c = (int64_t)n_clusters * C;
         } else {
             cudaGetLastError();
-            cap = (int64_t)per_sm * device_info().sm_count / C * C;
+            c = (int64_t)per_sm * device_info().sm_count / C * C;
         }
         const int64_t want = (int64_t)per_sm * device_info().sm_count;
-        if (cap > want) cap = want / C * C;
-        cap_smem = smem;
-        cap_c = C;
-    }
+        if (c > want) c = want / C * C;
+        return c;
+    });
     int64_t lim = cap;
     if (tl_grid_cap > 0 && tl_grid_cap < lim) lim = tl_grid_cap;
     int64_t grid = pa.n_batches < lim ? pa.n_batches : lim;

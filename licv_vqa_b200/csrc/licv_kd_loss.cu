@@ -125,10 +125,16 @@ __device__ __forceinline__ float tempered(float x, const RowConst& k) {
     return z;
 }
 
-template <int DT>
+// WANT_T: also d loss / d temperature (learnable_t, icv_module.py:49-52).  Both in-place divides by
+// T (icv_module.py:122-123) and the T^2 factor (:133) depend on it; with z = logits / T
+//   dKL_n/dT = -(1/T) [ sum_j (q_j W - w_j) zs_j + sum_j p_j (a_j - abar) zt_j ],
+//   a = ln(p+eps) - ln(q+eps) + p/(p+eps),  abar = sum_v p_v a_v = KL_n + sum_v p_v^2/(p_v+eps)
+// and d loss/dT = 2 T mean_n KL_n + T^2 mean_n dKL_n/dT.  Two more row sums in sweep 3 and one more
+// sweep; the row's dKL_n/dT goes to row_loss[2 n_rows + r], the total to out_losses[3].
+template <int DT, bool WANT_T>
 __global__ void __launch_bounds__(kThreads)
 kd_loss_generic_kernel(KdArgs a) {
-    __shared__ float slab[(kThreads / 32) * 4];
+    __shared__ float slab[(kThreads / 32) * 5];
     __shared__ int s_last;
     constexpr int EB = Fmt<DT>::kBytes;
 
@@ -149,6 +155,7 @@ kd_loss_generic_kernel(KdArgs a) {
                               : 0.f;
     float* row_kl = a.row_loss;
     float* row_ce = a.row_loss + a.n_rows;
+    float* row_dt = a.row_loss + 2 * a.n_rows;   // WANT_T only
 
     for (int64_t r = blockIdx.x; r < a.n_rows; r += gridDim.x) {
         const int64_t tr = !use_kl ? -1 : (a.kl_tea_row ? (int64_t)a.kl_tea_row[r] : r);
@@ -168,7 +175,11 @@ kd_loss_generic_kernel(KdArgs a) {
             if (grow) {
                 for (int j = threadIdx.x; j < a.vocab; j += blockDim.x) store_elem<DT>(grow, j, 0.f);
             }
-            if (threadIdx.x == 0) { row_kl[r] = 0.f; row_ce[r] = 0.f; }
+            if (threadIdx.x == 0) {
+                row_kl[r] = 0.f;
+                row_ce[r] = 0.f;
+                if (WANT_T) row_dt[r] = 0.f;
+            }
             continue;
         }
 
@@ -212,19 +223,45 @@ kd_loss_generic_kernel(KdArgs a) {
         const float inv_lce = 1.0f / sm[2];
 
         // ---- sweep 3 (L2): KL value and W_n --------------------------------------------------
-        float kw[2] = {0.f, 0.f};
+        float kw[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // KL/ln2, W; WANT_T: sum p^2/(p+eps), sum p a zt, sum p zt
         if (has_kl) {
             visit_row<DT, true>(xrow, trow, a.vocab, vec_ok, [&](int, float x, float t) {
                 const float q = ex2((tempered<DT>(x, k) - zs_max) * k.c2) * inv_ls;
-                const float p = ex2((tempered<DT>(t, k) - zt_max) * k.c2) * inv_lt;
+                const float zt = tempered<DT>(t, k);
+                const float p = ex2((zt - zt_max) * k.c2) * inv_lt;
                 const float rq = __frcp_rn(q + a.kl_eps);
                 // ln(p+eps) - ln(q+eps) = ln((p+eps)/(q+eps))
-                kw[0] = fmaf(p, lg2((p + a.kl_eps) * rq), kw[0]);
+                const float lr = lg2((p + a.kl_eps) * rq);
+                kw[0] = fmaf(p, lr, kw[0]);
                 kw[1] = fmaf(p * q, rq, kw[1]);
+                if (WANT_T) {
+                    const float ppe = p * __frcp_rn(p + a.kl_eps);
+                    kw[2] = fmaf(p, ppe, kw[2]);
+                    kw[3] = fmaf(p * fmaf(lr, kLn2, ppe), zt, kw[3]);
+                    kw[4] = fmaf(p, zt, kw[4]);
+                }
             });
-            cta_sum<2>(kw, slab);
+            cta_sum<5>(kw, slab);
         }
         const float W = kw[1];
+        if (WANT_T) {
+            // one more sweep, before the gradient may overwrite the row: sum_j (q_j W - w_j) zs_j
+            float s1[1] = {0.f};
+            if (has_kl) {
+                visit_row<DT, true>(xrow, trow, a.vocab, vec_ok, [&](int, float x, float t) {
+                    const float zs = tempered<DT>(x, k);
+                    const float q = ex2((zs - zs_max) * k.c2) * inv_ls;
+                    const float p = ex2((tempered<DT>(t, k) - zt_max) * k.c2) * inv_lt;
+                    const float w = p * q * __frcp_rn(q + a.kl_eps);
+                    s1[0] = fmaf(fmaf(q, W, -w), zs, s1[0]);
+                });
+                cta_sum<1>(s1, slab);
+            }
+            if (threadIdx.x == 0) {
+                const float abar = kw[0] * kLn2 + kw[2];
+                row_dt[r] = has_kl ? -(s1[0] + kw[3] - abar * kw[4]) / T : 0.f;
+            }
+        }
 
         // ---- sweep 4 (L2 read, HBM write): gradient ------------------------------------------
         if (grow) {
@@ -294,18 +331,21 @@ kd_loss_generic_kernel(KdArgs a) {
     __syncthreads();
     if (s_last) {
         __threadfence();
-        float tot[2] = {0.f, 0.f};
+        float tot[3] = {0.f, 0.f, 0.f};
         for (int64_t r = threadIdx.x; r < a.n_rows; r += blockDim.x) {
             tot[0] += __ldcg(row_kl + r);
             tot[1] += __ldcg(row_ce + r);
+            if (WANT_T) tot[2] += __ldcg(row_dt + r);
         }
-        cta_sum<2>(tot, slab);
+        cta_sum<3>(tot, slab);
         if (threadIdx.x == 0) {
             const float kl = use_kl ? tot[0] * T * T / (float)n_kl : 0.f;
             const float ce = use_ce ? tot[1] / (float)n_ce : 0.f;
             a.out_losses[0] = kl;
             a.out_losses[1] = ce;
             a.out_losses[2] = a.only_hard_loss ? ce : (use_ce ? fmaf(a.hard_loss_weight, ce, kl) : kl);
+            if (WANT_T)   // d(T^2 mean KL)/dT; zero when the KL term is switched off
+                a.out_losses[3] = use_kl ? (2.0f * T * tot[0] + T * T * tot[2]) / (float)n_kl : 0.f;
             *a.counter = 0u;  // leave the workspace ready for the next call
         }
     }
@@ -322,14 +362,22 @@ __global__ void scale_inplace_kernel(void* x, int64_t n, const float* scale) {
 
 }  // namespace
 
-int launch_kd_generic(const KdArgs& a, int dtype, cudaStream_t st) {
+int launch_kd_generic(const KdArgs& a, int dtype, cudaStream_t st, bool want_dtemp) {
     const int cap = device_info().sm_count * 2;
     int grid = (int)(a.n_rows < cap ? a.n_rows : cap);
     if (grid < 1) grid = 1;  // no rows: the finalising CTA still reports mean-of-empty = NaN
+    if (want_dtemp) {
+        switch (dtype) {
+            case LICV_F32: kd_loss_generic_kernel<LICV_F32, true><<<grid, kThreads, 0, st>>>(a); break;
+            case LICV_BF16: kd_loss_generic_kernel<LICV_BF16, true><<<grid, kThreads, 0, st>>>(a); break;
+            default: kd_loss_generic_kernel<LICV_F16, true><<<grid, kThreads, 0, st>>>(a); break;
+        }
+        return (int)cudaGetLastError();
+    }
     switch (dtype) {
-        case LICV_F32: kd_loss_generic_kernel<LICV_F32><<<grid, kThreads, 0, st>>>(a); break;
-        case LICV_BF16: kd_loss_generic_kernel<LICV_BF16><<<grid, kThreads, 0, st>>>(a); break;
-        default: kd_loss_generic_kernel<LICV_F16><<<grid, kThreads, 0, st>>>(a); break;
+        case LICV_F32: kd_loss_generic_kernel<LICV_F32, false><<<grid, kThreads, 0, st>>>(a); break;
+        case LICV_BF16: kd_loss_generic_kernel<LICV_BF16, false><<<grid, kThreads, 0, st>>>(a); break;
+        default: kd_loss_generic_kernel<LICV_F16, false><<<grid, kThreads, 0, st>>>(a); break;
     }
     return (int)cudaGetLastError();
 }
@@ -366,14 +414,14 @@ extern "C" int64_t licv_kd_loss_workspace_bytes(int64_t n_rows) {
     return 16 + ((2 * n_rows * (int64_t)sizeof(float) + 15) / 16) * 16;
 }
 
-extern "C" int licv_kd_loss_fwd_bwd(const void* stu, void* dstu, const void* tea,
-                                    const int32_t* kl_tea_row, const int64_t* ce_label,
-                                    const int32_t* counts, int64_t n_kl, int64_t n_ce,
-                                    float temperature, float kl_eps, float hard_loss_weight,
-                                    int only_hard_loss, float grad_scale, float* out_losses,
-                                    void* workspace, int64_t n_rows, int vocab, int64_t stu_stride,
-                                    int64_t tea_stride, int dtype, unsigned round_flags,
-                                    licv_stream_t stream) {
+static int kd_loss_entry(const void* stu, void* dstu, const void* tea,
+                         const int32_t* kl_tea_row, const int64_t* ce_label,
+                         const int32_t* counts, int64_t n_kl, int64_t n_ce,
+                         float temperature, float kl_eps, float hard_loss_weight,
+                         int only_hard_loss, float grad_scale, float* out_losses,
+                         void* workspace, int64_t n_rows, int vocab, int64_t stu_stride,
+                         int64_t tea_stride, int dtype, unsigned round_flags,
+                         licv_stream_t stream, bool want_dtemp) {
     if (device_info().status != LICV_OK) return device_info().status;
     if (dtype != LICV_F32 && dtype != LICV_BF16 && dtype != LICV_F16) return LICV_ERR_BAD_DTYPE;
     if (n_rows < 0 || vocab <= 0 || stu_stride < vocab || (tea && tea_stride < vocab))
@@ -400,13 +448,45 @@ extern "C" int licv_kd_loss_fwd_bwd(const void* stu, void* dstu, const void* tea
     a.n_rows = n_rows; a.vocab = vocab; a.stu_stride = stu_stride; a.tea_stride = tea_stride;
     a.round_flags = round_flags;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (want_dtemp) return launch_kd_generic(a, dtype, st, true);   // the generic kernel holds the logits it needs
     int C = 0, NV = 0, NT = 0;
     switch (kd_pick(vocab, dtype, temperature, ce_label != nullptr && !only_hard_loss, n_rows, &C, &NV, &NT)) {
         case LICV_KD_KERNEL_STREAM: return launch_kd_stream(a, dtype, st);
         case LICV_KD_KERNEL_TMEM: return launch_kd_tmem(a, dtype, st);
         case LICV_KD_KERNEL_CLUSTER: return launch_kd_cluster(a, dtype, C, NV, NT, st);
-        default: return launch_kd_generic(a, dtype, st);
+        default: return launch_kd_generic(a, dtype, st, false);
     }
+}
+
+extern "C" int licv_kd_loss_fwd_bwd(const void* stu, void* dstu, const void* tea,
+                                    const int32_t* kl_tea_row, const int64_t* ce_label,
+                                    const int32_t* counts, int64_t n_kl, int64_t n_ce,
+                                    float temperature, float kl_eps, float hard_loss_weight,
+                                    int only_hard_loss, float grad_scale, float* out_losses,
+                                    void* workspace, int64_t n_rows, int vocab, int64_t stu_stride,
+                                    int64_t tea_stride, int dtype, unsigned round_flags,
+                                    licv_stream_t stream) {
+    return kd_loss_entry(stu, dstu, tea, kl_tea_row, ce_label, counts, n_kl, n_ce, temperature, kl_eps,
+                         hard_loss_weight, only_hard_loss, grad_scale, out_losses, workspace, n_rows,
+                         vocab, stu_stride, tea_stride, dtype, round_flags, stream, false);
+}
+
+extern "C" int64_t licv_kd_loss_dtemp_workspace_bytes(int64_t n_rows) {
+    if (n_rows < 0) n_rows = 0;
+    return 16 + ((3 * n_rows * (int64_t)sizeof(float) + 15) / 16) * 16;
+}
+
+extern "C" int licv_kd_loss_fwd_bwd_dtemp(const void* stu, void* dstu, const void* tea,
+                                          const int32_t* kl_tea_row, const int64_t* ce_label,
+                                          const int32_t* counts, int64_t n_kl, int64_t n_ce,
+                                          float temperature, float kl_eps, float hard_loss_weight,
+                                          int only_hard_loss, float grad_scale, float* out_losses4,
+                                          void* workspace, int64_t n_rows, int vocab,
+                                          int64_t stu_stride, int64_t tea_stride, int dtype,
+                                          unsigned round_flags, licv_stream_t stream) {
+    return kd_loss_entry(stu, dstu, tea, kl_tea_row, ce_label, counts, n_kl, n_ce, temperature, kl_eps,
+                         hard_loss_weight, only_hard_loss, grad_scale, out_losses4, workspace, n_rows,
+                         vocab, stu_stride, tea_stride, dtype, round_flags, stream, true);
 }
 
 extern "C" int licv_scale_inplace(void* x, int64_t n, const float* scale, int dtype,

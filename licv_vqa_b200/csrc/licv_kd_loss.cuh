@@ -24,7 +24,7 @@ struct KdArgs {
     unsigned round_flags;
 };
 
-int launch_kd_generic(const KdArgs& a, int dtype, cudaStream_t st);
+int launch_kd_generic(const KdArgs& a, int dtype, cudaStream_t st, bool want_dtemp = false);
 
 // cluster kernel (licv_kd_loss_cluster.cu): does a row of `vocab` elements fit a cluster, and how
 bool kd_cluster_plan(int vocab, int dtype, float temperature, bool kl_and_ce, int* C, int* NV,

@@ -821,14 +821,14 @@ template <int DT, int NV, int NT>
 int launch_cluster(const KdArgs& a, int C, cudaStream_t st) {
     auto kern = kd_loss_cluster_kernel<DT, NV, NT>;
     constexpr size_t smem = (size_t)2 * NV * Fmt<DT>::kPerVec * NT * sizeof(float);
-    static bool raised = false;
-    if (!raised && smem > 48 * 1024) {
-        const cudaError_t e =
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
+    if (C > 8 || C < 1) return LICV_ERR_BAD_ARGUMENT;
+    static PerDevice<int> raised;
+    if (smem > 48 * 1024) {
+        const int e = raised.get([&] {
+            return (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        });
+        if (e != 0) return e;
     }
-    if (C > 8) return LICV_ERR_BAD_ARGUMENT;
-    raised = true;
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(NT);
     cfg.dynamicSmemBytes = smem;
@@ -836,24 +836,21 @@ int launch_cluster(const KdArgs& a, int C, cudaStream_t st) {
     cudaLaunchAttribute attr[2];
     cfg.attrs = attr;   // st.async / mapa are cluster instructions: C = 1 is launched as a cluster too
     cfg.numAttrs = launch_attrs(attr, C);
-    // clusters resident at once (per instantiation and cluster size; one process drives one GPU)
-    static int64_t cap[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (cap[C] == 0) {
+    // clusters resident at once (per instantiation, cluster size and device)
+    static PerDevice<int64_t> cap_by_c[9];
+    const int64_t cap_c = cap_by_c[C].get([&]() -> int64_t {
         int n = 0;
         cfg.gridDim = dim3(C * device_info().sm_count);
-        if (C > 1 && cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) {
-            cap[C] = n;
-        } else {
-            cudaGetLastError();
-            int per_sm = 1;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess ||
-                per_sm < 1)
-                per_sm = 1;
-            cap[C] = (int64_t)per_sm * device_info().sm_count / C;
-            if (cap[C] < 1) cap[C] = 1;
-        }
-    }
-    int64_t clusters = a.n_rows < cap[C] ? a.n_rows : cap[C];
+        if (C > 1 && cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) return n;
+        cudaGetLastError();
+        int per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess ||
+            per_sm < 1)
+            per_sm = 1;
+        const int64_t c = (int64_t)per_sm * device_info().sm_count / C;
+        return c < 1 ? 1 : c;
+    });
+    int64_t clusters = a.n_rows < cap_c ? a.n_rows : cap_c;
     if (clusters < 1) clusters = 1;   // no rows: the finalising CTA still reports mean-of-empty
     cfg.gridDim = dim3((unsigned)(clusters * C));
     return (int)cudaLaunchKernelEx(&cfg, kern, a);
@@ -879,13 +876,11 @@ template <int DT, int MT, int MNV>
 int launch_tmem(const KdArgs& a, cudaStream_t st) {
     auto kern = kd_loss_tmem_kernel<DT, MT, MNV>;
     constexpr size_t smem = (size_t)MNV * 2 * MT * sizeof(float4);   // e_s: 128-144 KB
-    static bool raised = false;
-    if (!raised) {
-        const cudaError_t e =
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        raised = true;
-    }
+    static PerDevice<int> raised;
+    const int e = raised.get([&] {
+        return (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    });
+    if (e != 0) return e;
     int64_t grid = a.n_rows < device_info().sm_count ? a.n_rows : device_info().sm_count;
     if (grid < 1) grid = 1;
     cudaLaunchConfig_t cfg = {};

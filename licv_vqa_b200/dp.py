@@ -296,7 +296,11 @@ class ICVDataParallelOptimizer:
         f = cosine_warmup_factor(self.step_no, self.warm_steps, self.total_steps)
         return self.icv_lr * f, self.alpha_lr * f
 
-    def step(self, logged: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+    def step(self, logged: Optional[Dict[str, torch.Tensor]] = None, module=None) -> Dict[str, torch.Tensor]:
+        """``module``: the VQAICVModule whose `global_step` this optimizer step advances (what
+        Lightning does for the reference; the temperature schedule counts in it)."""
+        if module is not None and hasattr(module, "on_optimizer_step"):
+            module.on_optimizer_step()
         st = self.state
         if not st.param.is_cuda:
             raise RuntimeError("ICVDataParallelOptimizer.step runs the fused sm_100a optimizer "

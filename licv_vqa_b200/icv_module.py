@@ -55,7 +55,7 @@ class ModuleConfig:
     icv_encoder: ICVEncoderConfig = field(default_factory=ICVEncoderConfig)
     # --- additions of this implementation (defaults keep the reference's semantics) ---
     ce_variant: str = "auto"            # "idefics" | "idefics2" | "causal_lm" | "auto" (by lmm name)
-    image_token_id: int = -1            # idefics2: label id ignored by its CE
+    image_token_id: int = -1            # idefics2: label id ignored by its CE (-1: the tower's config)
     # the reference enables activation checkpointing whenever the tower supports it
     # (icv_module.py:29-30); "reentrant" / "non_reentrant" pick torch.utils.checkpoint's mode
     # (True = the installed transformers' default), False turns it off
@@ -130,12 +130,12 @@ class VQAICVModule(nn.Module):
             use_sigmoid=_get(enc_cfg, "use_sigmoid", False),
         )
 
-        if _get(self.module_cfg, "learnable_t", False):
-            # d loss / d temperature is outside the hot path this build covers (default False in
-            # the reference, config/icv_module/icv_module.yaml:11)
-            raise NotImplementedError("learnable_t=True is not supported by the fused loss")
+        # icv_module.py:49-52.  learnable_t: d loss / d T comes out of the loss launch (the generic
+        # kernel) and the value is read from the device once per step; otherwise the kernels take
+        # T from the host mirror and nothing synchronises
         init_t = float(_get(self.module_cfg, "init_temperature", 1.0))
-        self.temperature = torch.nn.Parameter(torch.tensor(init_t), requires_grad=False)
+        self.learnable_t = bool(_get(self.module_cfg, "learnable_t", False))
+        self.temperature = torch.nn.Parameter(torch.tensor(init_t), requires_grad=self.learnable_t)
         self._temperature_value = init_t  # host mirror: the kernels take T by value, no sync
         self.decay_per_step = None
         self.global_step = 0
@@ -145,6 +145,11 @@ class VQAICVModule(nn.Module):
         self._temperature_value = float(value)
         with torch.no_grad():
             self.temperature.fill_(float(value))
+
+    def _temperature(self):
+        """What the loss takes as T: the Parameter itself when it is learnable (its gradient is
+        wanted and its value lives on the device), else the host mirror."""
+        return self.temperature if self.learnable_t else self._temperature_value
 
     def setup_temperature_decay(self, estimated_stepping_batches: int):
         """on_train_start (icv_module.py:54-69)."""
@@ -164,6 +169,11 @@ class VQAICVModule(nn.Module):
         ratio = _get(self.module_cfg, "decay_ratio", -1)
         if ratio < 0:
             return
+        if self.decay_per_step is None:
+            if self.setup_temperature_decay(0) in (None, -1) or not self.decay_per_step:
+                raise RuntimeError("decay_ratio is set but the decay period is not: call "
+                                   "setup_temperature_decay(estimated_stepping_batches) first "
+                                   "(on_train_start in the reference, icv_module.py:54-69)")
         if self.global_step % self.decay_per_step == 0 and self.global_step != 0:
             self.set_temperature(max(self._temperature_value * ratio,
                                      _get(self.module_cfg, "min_tmeprature", 1.0)))
@@ -179,6 +189,16 @@ class VQAICVModule(nn.Module):
         if "idefics" in name:
             return "idefics"
         return "causal_lm"
+
+    def _image_token_id(self):
+        """idefics2's CE ignores the image token (HF: CrossEntropyLoss(ignore_index=image_token_id));
+        taken from the tower's config unless the module config names it."""
+        tid = int(_get(self.module_cfg, "image_token_id", -1))
+        if tid >= 0:
+            return tid
+        conf = getattr(getattr(self.interface, "model", None), "config", None)
+        tid = getattr(conf, "image_token_id", None)
+        return int(tid) if isinstance(tid, int) and tid >= 0 else -1
 
     def forward(self, query_inputs, inputs, query_x_length, in_context_length):
         """One student pass (hooks on) + one teacher pass (hooks off, no grad) + the fused loss.
@@ -208,7 +228,7 @@ class VQAICVModule(nn.Module):
             _, ce_label, counts = ops.kd_prepare_rows(
                 stu_ids, query_x_length, stu_ids, query_x_length, pad_id,
                 query_inputs.get("attention_mask"), self._ce_variant(),
-                _get(cfg, "image_token_id", -1), want_ce=True)
+                self._image_token_id(), want_ce=True)
             total, _, _ = ops.kd_loss(icv_logits.view(-1, V), None, None, ce_label, counts,
                                       temperature=self._temperature_value, only_hard_loss=True)
             return {"loss": total}, icv_encoder_output
@@ -217,7 +237,7 @@ class VQAICVModule(nn.Module):
         prep = ops.kd_prepare_rows(
             stu_ids, query_x_length, inputs[ids_name], in_context_length, pad_id,
             query_inputs.get("attention_mask"), self._ce_variant(),
-            _get(cfg, "image_token_id", -1), want_ce=want_ce, compact_teacher=compact)
+            self._image_token_id(), want_ce=want_ce, compact_teacher=compact)
         kl_tea_row, ce_label, counts = prep[:3]
         with torch.no_grad():
             self.icv_model.toggle_intervention(False)
@@ -234,7 +254,7 @@ class VQAICVModule(nn.Module):
                                    f"({n_s}) at non-singleton dimension 0")
         total, kl, ce = ops.kd_loss(
             icv_logits.view(-1, V), ice_logits.view(-1, V), kl_tea_row, ce_label, counts,
-            temperature=self._temperature_value, kl_eps=float(_get(cfg, "kl_eps", 1e-6)),
+            temperature=self._temperature(), kl_eps=float(_get(cfg, "kl_eps", 1e-6)),
             hard_loss_weight=hard_w)
         loss_dict = {"kl_loss": kl}
         if want_ce:
@@ -282,7 +302,7 @@ class VQAICVModule(nn.Module):
         stu_logits / tea_logits [N,V].  Like the reference this consumes its arguments: the
         student logits' storage is overwritten (here with the gradient, there with logits/T)."""
         total, _, _ = ops.kd_loss(stu_logits, tea_logits.detach(),
-                                  temperature=self._temperature_value,
+                                  temperature=self._temperature(),
                                   kl_eps=float(_get(self.module_cfg, "kl_eps", 1e-6)))
         return total
 
@@ -296,6 +316,12 @@ class VQAICVModule(nn.Module):
         self.decay_temperature()
         loss_dict, _ = self(**batch)
         return loss_dict["loss"], loss_dict
+
+    def on_optimizer_step(self):
+        """Lightning advances `global_step` once per optimizer step; without Lightning the training
+        loop (or ICVDataParallelOptimizer.step(module=...)) calls this - the temperature schedule
+        (icv_module.py:150-158) counts in it."""
+        self.global_step += 1
 
     # ------------------------------------------------------------------ checkpoint (f3)
     def icv_checkpoint(self):

@@ -334,24 +334,42 @@ def kd_prepare_rows(stu_ids, stu_mask_length, tea_ids, tea_mask_length, pad_toke
 # a7 + a8 + a9 + a10: distillation loss
 # ---------------------------------------------------------------------------------------------
 _WS_CACHE: dict = {}
+_OPT_WS_CACHE: dict = {}
+_WS_CACHE_MAX = 32      # (device, stream) pairs kept; the oldest entry goes first
 
 
-def _workspace(device, n_rows):
-    """Per-(device, stream) workspace, grown on demand; its 16-byte header stays zero between
-    calls (the kernel restores it)."""
-    key = (device.index, _stream())
-    need = _abi.load().licv_kd_loss_workspace_bytes(int(n_rows))
-    ws = _WS_CACHE.get(key)
+def _cached(cache, key, need, device):
+    """A zero-initialised scratch tensor per (device, stream).  It is allocated while that stream
+    is current, so dropping it later is ordered after the stream's kernels; the calling thread
+    owns its entry - two threads on two streams never share one."""
+    ws = cache.get(key)
     if ws is None or ws.numel() < need:
-        ws = torch.zeros(max(need, 4096), dtype=torch.uint8, device=device)
-        _WS_CACHE[key] = ws
+        if ws is None and len(cache) >= _WS_CACHE_MAX:
+            cache.pop(next(iter(cache)))
+        ws = torch.zeros(max(need, 64), dtype=torch.uint8, device=device)
+        cache[key] = ws
     return ws
+
+
+def _workspace(device, n_rows, dtemp=False):
+    """Loss-kernel workspace per (device, stream), grown on demand; its 16-byte header stays zero
+    between calls (the kernel restores it)."""
+    lib = _abi.load()
+    need = (lib.licv_kd_loss_dtemp_workspace_bytes if dtemp else lib.licv_kd_loss_workspace_bytes)(int(n_rows))
+    return _cached(_WS_CACHE, (device.index, _stream()), max(need, 4096), device)
+
+
+def _optimizer_workspace(device):
+    """The optimizer's own 16 bytes (sum of squares + ticket, zero between calls)."""
+    return _cached(_OPT_WS_CACHE, (device.index, _stream()), 16, device)
 
 
 def kd_loss_raw(stu, tea, kl_tea_row=None, ce_label=None, counts=None, n_kl=0, n_ce=0,
                 temperature=1.0, kl_eps=1e-6, hard_loss_weight=0.0, only_hard_loss=False,
-                grad_scale=1.0, in_place=True, want_grad=True, round_flags=_abi.ROUND_TEMPERED):
-    """One launch: losses [3] = (kl, ce, total) and d total / d stu.
+                grad_scale=1.0, in_place=True, want_grad=True, round_flags=_abi.ROUND_TEMPERED,
+                want_dtemp=False):
+    """One launch: losses [3] = (kl, ce, total) and d total / d stu.  ``want_dtemp``: losses [4],
+    the last entry d total / d temperature (learnable_t, icv_module.py:49-52).
 
     stu [R,V] (last dim contiguous, rows strided), tea [Rt,V].  With ``in_place`` the gradient
     overwrites ``stu``'s storage (the student logits are dead after the loss; the reference
@@ -363,13 +381,14 @@ def kd_loss_raw(stu, tea, kl_tea_row=None, ce_label=None, counts=None, n_kl=0, n
     if tea is not None:
         if tea.dim() != 2 or tea.stride(1) != 1 or tea.shape[1] != V or tea.dtype != stu.dtype:
             raise ValueError("tea must be [Rt,V] of the student's dtype with a contiguous last dim")
-    losses = torch.empty(3, dtype=torch.float32, device=stu.device)
+    losses = torch.empty(4 if want_dtemp else 3, dtype=torch.float32, device=stu.device)
     dstu = None
     if want_grad:
         dstu = stu if in_place else torch.empty_strided(stu.shape, stu.stride(), dtype=stu.dtype,
                                                         device=stu.device)
-    ws = _workspace(stu.device, R)
-    _abi.check(_abi.load().licv_kd_loss_fwd_bwd(
+    ws = _workspace(stu.device, R, want_dtemp)
+    entry = _abi.load().licv_kd_loss_fwd_bwd_dtemp if want_dtemp else _abi.load().licv_kd_loss_fwd_bwd
+    _abi.check(entry(
         stu.data_ptr(), _ptr(dstu), _ptr(tea), _ptr(kl_tea_row), _ptr(ce_label), _ptr(counts),
         int(n_kl), int(n_ce), float(temperature), float(kl_eps), float(hard_loss_weight),
         int(bool(only_hard_loss)), float(grad_scale), losses.data_ptr(), ws.data_ptr(), R, V,
@@ -381,13 +400,15 @@ def kd_loss_raw(stu, tea, kl_tea_row=None, ce_label=None, counts=None, n_kl=0, n
 class _KDLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, stu, tea, kl_tea_row, ce_label, counts, n_kl, n_ce, temperature, kl_eps,
-                hard_loss_weight, only_hard_loss, in_place, round_flags):
+                hard_loss_weight, only_hard_loss, in_place, round_flags, t_param):
         need = stu.requires_grad
         src = stu.detach()
+        want_dtemp = t_param is not None and t_param.requires_grad
         losses, dstu = kd_loss_raw(src, tea, kl_tea_row, ce_label, counts, n_kl, n_ce, temperature,
                                    kl_eps, hard_loss_weight, only_hard_loss, 1.0, in_place, need,
-                                   round_flags)
+                                   round_flags, want_dtemp)
         ctx.dstu = dstu
+        ctx.dtemp = losses[3].clone() if want_dtemp else None
         if in_place and need:
             # stu's storage now holds the gradient: bump its version so autograd refuses, loudly,
             # any other backward that saved the logits themselves
@@ -400,8 +421,11 @@ class _KDLoss(torch.autograd.Function):
     def backward(ctx, g_total, _g_kl, _g_ce):
         dstu = ctx.dstu
         ctx.dstu = None
+        d_t = None
+        if ctx.dtemp is not None:
+            d_t = (ctx.dtemp * g_total.detach().float()).reshape(())
         if dstu is None:
-            return (None,) * 13
+            return (None,) * 13 + (d_t,)
         # upstream gradient of the scalar loss: applied in place, and skipped on the device
         # (no traffic, no host sync) when it is exactly 1
         g = g_total.detach().to(torch.float32).contiguous()
@@ -411,7 +435,7 @@ class _KDLoss(torch.autograd.Function):
                        "licv_scale_inplace")
         else:  # padded row stride: rare, plain torch
             dstu.mul_(g.to(dstu.dtype))
-        return (dstu,) + (None,) * 12
+        return (dstu,) + (None,) * 12 + (d_t,)
 
 
 def kd_loss(stu, tea, kl_tea_row=None, ce_label=None, counts=None, n_kl=None, n_ce=None,
@@ -423,8 +447,15 @@ def kd_loss(stu, tea, kl_tea_row=None, ce_label=None, counts=None, n_kl=None, n_
     (None/None = the compact form ``calculate_kl_divergence`` takes: row r vs teacher row r, no
     CE).  ``counts`` (device) or ``n_kl``/``n_ce`` (host ints) give the means' denominators.
     With ``in_place`` (default) the gradient is written over ``stu``'s storage, so ``stu`` must
-    not be read after this call.
+    not be read after this call.  ``temperature`` may be the module's Parameter: when it
+    requires grad (learnable_t) its gradient is computed too, at the price of the generic kernel
+    and of one host read of its value per call.
     """
+    t_param = None
+    if isinstance(temperature, torch.Tensor):
+        if temperature.requires_grad and torch.is_grad_enabled():
+            t_param = temperature
+        temperature = float(temperature.detach())
     R = stu.shape[0]
     if counts is None:
         if n_kl is None:
@@ -435,7 +466,7 @@ def kd_loss(stu, tea, kl_tea_row=None, ce_label=None, counts=None, n_kl=None, n_
             raise ValueError("give `counts` (device) or both n_kl and n_ce (host) with row lists")
     return _KDLoss.apply(stu, tea, kl_tea_row, ce_label, counts, n_kl or 0, n_ce or 0,
                          float(temperature), float(kl_eps), float(hard_loss_weight),
-                         bool(only_hard_loss), bool(in_place), int(round_flags))
+                         bool(only_hard_loss), bool(in_place), int(round_flags), t_param)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -446,11 +477,8 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, n_vec, n_alpha, lr_vec, lr_alph
                max_grad_norm=1.0, norm_out=None, workspace=None):
     _need_cuda(param, grad, exp_avg, exp_avg_sq)
     if workspace is None:
-        workspace = _workspace(param.device, 0)
-        # the optimizer uses bytes [8,16) of the shared zeroed header
-        ws_ptr = workspace.data_ptr() + 8
-    else:
-        ws_ptr = workspace.data_ptr()
+        workspace = _optimizer_workspace(param.device)
+    ws_ptr = workspace.data_ptr()
     _abi.check(_abi.load().licv_adamw_step(
         param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), int(n_vec),
         int(n_alpha), float(lr_vec), float(lr_alpha), float(beta1), float(beta2), float(eps),

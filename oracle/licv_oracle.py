@@ -219,7 +219,8 @@ def _tempered(x, T, logit_fmt):
     return z
 
 
-def kl_divergence(stu, tea, temperature=1.0, kl_eps=1e-6, need_grad=True, logit_fmt=None):
+def kl_divergence(stu, tea, temperature=1.0, kl_eps=1e-6, need_grad=True, logit_fmt=None,
+                  want_dtemp=False):
     """T^2 * mean_n sum_v p (log(p+eps) - log(q+eps)),  p=softmax(tea/T), q=softmax(stu/T).
 
     stu, tea [N,V].  Returns (loss, d_stu [N,V] or None); d_stu[n,j] = (T/N)(q_j W_n - w_j),
@@ -241,7 +242,17 @@ def kl_divergence(stu, tea, temperature=1.0, kl_eps=1e-6, need_grad=True, logit_
     w = p * q / (q + kl_eps)
     W = w.sum(-1, keepdims=True)
     d_stu = (T / max(n, 1)) * (q * W - w)
-    return loss, d_stu
+    if not want_dtemp:
+        return loss, d_stu
+    # learnable_t (icv_module.py:49-52): BOTH in-place divides (:122-123) and the T**2 factor (:133)
+    # depend on T.  With z = x / T:  dKL_n/dT = -(1/T) [ sum_j dKL/dzs_j zs_j + sum_j dKL/dzt_j zt_j ],
+    # dKL/dzs = q W - w,  dKL/dzt_j = p_j (a_j - sum_v p_v a_v),  a = log(p+eps) - log(q+eps) + p/(p+eps)
+    zs, zt = _tempered(stu, T, logit_fmt), _tempered(tea, T, logit_fmt)
+    a = np.log(p + kl_eps) - np.log(q + kl_eps) + p / (p + kl_eps)
+    g_t = p * (a - (p * a).sum(-1, keepdims=True))
+    dkl = -(((q * W - w) * zs).sum(-1) + (g_t * zt).sum(-1)) / T
+    d_temp = 2.0 * T * per_row.mean() + T * T * dkl.mean() if n else np.float64("nan")
+    return loss, d_stu, d_temp
 
 
 # --------------------------------------------------------------------------------------------

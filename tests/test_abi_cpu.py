@@ -200,8 +200,24 @@ def test_checkpoint_wire_format_round_trip(tmp_path):
         dec.decay_temperature()
         seen.append(dec._temperature_value)
     assert seen == [4.0, 4.0, 2.0, 2.0, 1.5, 1.5, 1.5] and float(dec.temperature) == 1.5
-    with pytest.raises(NotImplementedError):
-        VQAICVModule(Iface(), ModuleConfig(learnable_t=True), lmm)
+    # the schedule counts optimizer steps (Lightning's global_step in the reference)
+    dec2 = VQAICVModule(Iface(), ModuleConfig(init_temperature=4.0, decay_ratio=0.5, decay_per_step=2,
+                                              min_tmeprature=1.5), lmm)
+    dec2.setup_temperature_decay(100)
+    seen = []
+    for _ in range(5):
+        dec2.decay_temperature()
+        seen.append(dec2._temperature_value)
+        dec2.on_optimizer_step()
+    assert seen == [4.0, 4.0, 2.0, 2.0, 1.5]
+    # a decay ratio without a period is a configuration error, said clearly
+    bad = VQAICVModule(Iface(), ModuleConfig(init_temperature=4.0, decay_ratio=0.5, decay_per_step=-1), lmm)
+    with pytest.raises(RuntimeError, match="decay period"):
+        bad.decay_temperature()
+    # learnable_t (icv_module.py:49-52): the temperature is a trainable parameter
+    lt = VQAICVModule(Iface(), ModuleConfig(learnable_t=True, init_temperature=2.0), lmm)
+    assert lt.temperature.requires_grad and float(lt.temperature) == 2.0
+    assert "temperature" in [k for k, p in lt.named_parameters() if p.requires_grad]
 
 
 def test_collator_contract_from_token_ids():

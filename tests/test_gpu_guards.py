@@ -114,3 +114,51 @@ def test_kd_loss_stays_inside_its_rows(ops, dt, V, R, Rt, pad_s, pad_t):
                           logit_fmt=None if dt == "fp32" else dt)
     assert abs(float(losses[2]) - want["loss"]) <= 1e-5 * abs(want["loss"])    # no NaN leaked in
     assert rel_err(host(dstu), want["d_stu"]) < (1e-5 if dt == "fp32" else 1.2 * EPS[dt])
+
+
+def test_two_threads_two_streams_give_the_single_thread_results():
+    """The entry points are re-entrant (backward runs on autograd's own thread, on
+    whatever stream is current there): two host threads, each on its own stream with its own
+    tensors, running injection fwd/bwd and the loss at the same time give exactly what one thread
+    gives."""
+    import threading
+
+    import numpy as np
+    from licv_vqa_b200 import ops
+
+    def work(seed, out, use_stream):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        h = (torch.randn(300, 4096, device="cuda", generator=g) * 4).to(torch.bfloat16)
+        gr = torch.randn(300, 4096, device="cuda", generator=g).to(torch.bfloat16)
+        s = torch.randn(4096, device="cuda", generator=g)
+        stu = (torch.randn(600, 32002, device="cuda", generator=g) * 3).to(torch.bfloat16)
+        tea = (torch.randn(600, 32002, device="cuda", generator=g) * 3).to(torch.bfloat16)
+        lab = torch.randint(0, 32002, (600,), device="cuda", generator=g)
+        torch.cuda.synchronize()
+        stream = torch.cuda.Stream() if use_stream else torch.cuda.current_stream()
+        with torch.cuda.stream(stream):
+            res = []
+            for _ in range(6):
+                o = ops.inject_forward(h, s)
+                ds = torch.zeros(4096, device="cuda")
+                dh = ops.inject_backward(h, gr, s, ds, True, 0)
+                losses, dstu = ops.kd_loss_raw(stu, tea, None, lab, None, 600, 600, 1.0, 1e-6, 0.5,
+                                               in_place=False)
+                res = [o, dh, ds, losses, dstu]
+            stream.synchronize()
+        out[seed] = [t.float().cpu().numpy() for t in res]
+
+    ref, got = {}, {}
+    for seed in (1, 2):
+        work(seed, ref, False)
+    threads = [threading.Thread(target=work, args=(seed, got, True)) for seed in (1, 2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for seed in (1, 2):
+        for a, b, exact in zip(ref[seed], got[seed], (True, True, False, True, True)):
+            if exact:
+                assert np.array_equal(a, b)
+            else:   # d_shift: fp32 atomics, summation order
+                assert np.allclose(a, b, rtol=1e-5, atol=1e-5)

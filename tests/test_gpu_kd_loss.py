@@ -320,3 +320,26 @@ def test_kd_loss_config1_training_shape_in_place(ops):
     dead = (ktr < 0) & (lab == -100)
     assert not host(dstu)[dead].any()
 
+
+
+DTEMP = load_golden("kl_dtemp_cases.npz")
+
+
+@pytest.mark.parametrize("name", [str(n) for n in DTEMP["names"]])
+def test_learnable_temperature_gradient_matches_reference(ops, name):
+    """learnable_t=True (icv_module.py:49-52): d loss / d T through both in-place divides and the
+    T**2 factor, against the reference's own autograd (tests/golden/kl_dtemp_cases.npz) at the
+    stated 1e-4 and against the oracle's closed form."""
+    T, eps = DTEMP[f"{name}/params"]
+    stu = dev(DTEMP[f"{name}/stu"], torch.float32).requires_grad_(True)
+    tea = dev(DTEMP[f"{name}/tea"], torch.float32)
+    t_param = torch.nn.Parameter(torch.tensor(float(T), device="cuda"))
+    logits = stu * 1.0
+    total, kl, _ = ops.kd_loss(logits, tea, temperature=t_param, kl_eps=float(eps), in_place=False)
+    (total * 3.0).backward()                      # an upstream factor reaches dT as well
+    ref_loss, ref_dt = float(DTEMP[f"{name}/loss"]), float(DTEMP[f"{name}/dtemp"])
+    assert abs(float(total) - ref_loss) <= 1e-4 * abs(ref_loss)
+    assert abs(float(t_param.grad) / 3.0 - ref_dt) <= 1e-4 * abs(ref_dt) + 1e-7
+    assert rel_err(host(stu.grad) / 3.0, DTEMP[f"{name}/dstu"]) < 1e-4
+    _, _, o_dt = O.kl_divergence(DTEMP[f"{name}/stu"], DTEMP[f"{name}/tea"], T, eps, want_dtemp=True)
+    assert abs(float(t_param.grad) / 3.0 - o_dt) <= 2e-5 * abs(o_dt) + 1e-7

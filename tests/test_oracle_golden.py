@@ -194,3 +194,14 @@ def test_inject_nan_when_shift_cancels_token():
     s = np.array([-1.0, 2.0, -3.0])
     out = O.inject_fwd(h, s)
     assert np.isnan(out[0]).all() and np.isfinite(out[1]).all()
+
+
+def test_oracle_temperature_gradient_matches_reference_golden():
+    """d loss / d T of the oracle against the reference's autograd (learnable_t, icv_module.py:49-52)."""
+    G = load_golden("kl_dtemp_cases.npz")
+    for name in [str(n) for n in G["names"]]:
+        T, eps = G[f"{name}/params"]
+        loss, d_stu, d_t = O.kl_divergence(G[f"{name}/stu"], G[f"{name}/tea"], T, eps, want_dtemp=True)
+        assert abs(loss - float(G[f"{name}/loss"])) <= 1e-5 * abs(loss)
+        assert abs(d_t - float(G[f"{name}/dtemp"])) <= 2e-5 * abs(d_t) + 1e-7
+        assert rel_err(d_stu, G[f"{name}/dstu"]) < 1e-5

@@ -153,7 +153,8 @@ class PeerExchange:
             if self.world == 1:
                 ok = failure is None
             else:
-                flag = torch.tensor([0.0 if failure else 1.0], device="cuda")
+                where = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+                flag = torch.tensor([0.0 if failure else 1.0], device=where)
                 dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
                 ok = bool(flag.item() == 1.0)
             if not ok:
@@ -169,7 +170,9 @@ class PeerExchange:
         agree("region")
         handles = handle.raw
         if self.world > 1:
-            mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).cuda()
+            mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8)
+            if dist.get_backend(group) == "nccl":
+                mine = mine.cuda()
             every = [torch.empty_like(mine) for _ in range(self.world)]
             dist.all_gather(every, mine, group=group)
             handles = b"".join(bytes(t.cpu().tolist()) for t in every)

@@ -108,6 +108,23 @@ def load_reference_module_methods(names=("forward", "calculate_kl_divergence", "
     return out
 
 
+def load_reference_collator():
+    """The reference's own ``collator_data`` (icv_src/icv_datamodule.py:73-130), AST-extracted: the
+    module imports pytorch_lightning / lmm_icl_interface at its top, the function itself needs
+    only a prompt processor with ``prepare_input``, ``input_ids_field`` and ``tokenizer``."""
+    path = os.path.join(REFERENCE_ROOT, "icv_src", "icv_datamodule.py")
+    with open(path) as f:
+        src = f.read()
+    tree = ast.parse(src)
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == "collator_data":
+            code = "from __future__ import annotations\n" + textwrap.dedent(ast.get_source_segment(src, node))
+            ns = {"torch": torch}
+            exec(compile(code, f"{path}:collator_data", "exec"), ns)
+            return ns["collator_data"]
+    raise RuntimeError(f"could not extract collator_data from {path}")
+
+
 class InterfaceStandIn(nn.Module):
     """Duck-typed ``lmm_icl_interface.LMMInterface``: only the attributes the hot path touches
     (``icv_module.py:28-30,137-146``, ``icv_intervention.py:46,113,129``)."""

@@ -275,3 +275,35 @@ def test_kd_loss_plan_fast_kernel_for_reference_vocabularies():
     assert lib.licv_kd_loss_plan(50257, _abi.BF16, 2.0, 1, 8192) == _abi.KD_KERNEL_GENERIC
     assert lib.licv_kd_loss_plan(300000, _abi.BF16, 1.0, 0, 8192) == _abi.KD_KERNEL_GENERIC
     assert lib.licv_kd_loss_plan(0, _abi.BF16, 1.0, 0, 8192) < 0
+
+
+def test_collator_matches_the_references_collator_over_a_real_tokenizer():
+    """f4 pinned: tests/golden/collator_cases.npz is the output of the reference's own, unmodified
+    collator_data (icv_datamodule.py:73-130) driven by a real transformers fast tokenizer (built
+    in process by oracle/make_golden.py: LLaMA / idefics-style BOS, EOS, pad = <unk>, image
+    tokens; right and left padding).  collate_token_ids, fed the per-sample id lists a dataset
+    that tokenises each part once would hold, must reproduce all four outputs bit for bit."""
+    import numpy as np
+    from licv_vqa_b200.collate import check_batch_contract, collate_token_ids
+    from tests.util import load_golden
+    G = load_golden("collator_cases.npz")
+    for name in [str(n) for n in G["names"]]:
+        pad, bos, eos = [int(x) for x in G[f"{name}/special_ids"]]
+        n = int(G[f"{name}/n_samples"])
+        q = [G[f"{name}/sample{b}/query_ids"].tolist() for b in range(n)]
+        qx = [G[f"{name}/sample{b}/query_x_ids"].tolist() for b in range(n)]
+        ice = [G[f"{name}/sample{b}/ice_ids"].tolist() for b in range(n)]
+        side = "left" if name.endswith("left") else "right"
+        batch = collate_token_ids(q, qx, ice, pad, bos, eos, padding_side=side)
+        assert np.array_equal(batch["query_inputs"]["input_ids"].numpy(), G[f"{name}/q_ids"])
+        assert np.array_equal(batch["query_inputs"]["attention_mask"].numpy(), G[f"{name}/q_att"])
+        assert np.array_equal(batch["inputs"]["input_ids"].numpy(), G[f"{name}/t_ids"])
+        assert np.array_equal(batch["inputs"]["attention_mask"].numpy(), G[f"{name}/t_att"])
+        assert np.array_equal(batch["in_context_length"].numpy(), G[f"{name}/in_context_length"])
+        assert np.array_equal(batch["query_x_length"].numpy(), G[f"{name}/query_x_length"])
+        if side == "right":
+            # the lengths are token COUNTS used as positions (icv_module.py:136-148): with right
+            # padding both masks select the answer tokens + EOS of every sample
+            n_rows = check_batch_contract(batch, pad)
+            want = sum(len(a) - len(b) + 1 for a, b in zip(q, qx))
+            assert n_rows == want

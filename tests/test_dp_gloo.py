@@ -152,3 +152,66 @@ def test_rebind_keeps_gradients_that_autograd_put_in_fresh_tensors():
     ((enc.icv * gv).sum() + (enc.alpha * ga).sum()).backward()
     st.rebind()
     assert torch.allclose(st.grad[:st.n_vec].view(1, L, D), 2 * gv)
+
+
+class _FakeLib:
+    """liblicv_b200's peer-exchange set-up calls with a failure injected on one rank."""
+
+    def __init__(self, fail_rank, stage, rank, log):
+        self.fail_rank, self.stage, self.rank, self.log = fail_rank, stage, rank, log
+
+    def licv_dp_region_alloc(self, n, region_ref, handle):
+        if self.stage == "alloc" and self.rank == self.fail_rank:
+            return 2          # cudaErrorMemoryAllocation
+        region_ref._obj.value = 0x1000 + self.rank
+        return 0
+
+    def licv_dp_comm_create(self, comm_ref, rank, world, region, handles, n):
+        if self.stage == "map" and self.rank == self.fail_rank:
+            return 101        # an IPC handle that can not be opened
+        comm_ref._obj.value = 0x2000 + self.rank
+        return 0
+
+    def licv_dp_region_free(self, region):
+        self.log.append("freed")
+        return 0
+
+
+def _consensus_worker(rank, world, port, out_dir, stage):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from licv_vqa_b200 import _abi, dp
+        log = []
+        fake = _FakeLib(1, stage, rank, log)
+        _abi_load, _abi_status = _abi.load, _abi.status_string
+        _abi.load = lambda *a, **k: fake
+        _abi.status_string = lambda rc: f"status {rc}"
+        try:
+            try:
+                dp.PeerExchange(100)
+                outcome = "created"
+            except RuntimeError as exc:
+                outcome = "raised: " + str(exc)
+        finally:
+            _abi.load, _abi.status_string = _abi_load, _abi_status
+        with open(os.path.join(out_dir, f"{stage}{rank}.txt"), "w") as f:
+            f.write(outcome + "|" + ",".join(log))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("stage", ["alloc", "map"])
+def test_peer_exchange_setup_failure_on_one_rank_raises_on_every_rank(tmp_path, stage):
+    """A rank that can not allocate or map its peers must not fall back on its own: every rank
+    learns of it (one MIN all-reduce) and raises, so `exchange="auto"` takes the NCCL path on all
+    of them - nobody is left spinning on packets that never come.  The region is given back."""
+    world, port = 2, _free_port()
+    mp.spawn(_consensus_worker, args=(world, port, str(tmp_path), stage), nprocs=world, join=True)
+    out = [open(tmp_path / f"{stage}{r}.txt").read() for r in range(world)]
+    assert all(o.startswith("raised: peer-memory exchange unavailable") for o in out), out
+    assert "another rank failed" in out[0]                     # the healthy rank says why
+    assert ("licv_dp_region_alloc" if stage == "alloc" else "licv_dp_comm_create") in out[1]
+    if stage == "map":
+        assert out[0].endswith("freed") and out[1].endswith("freed")

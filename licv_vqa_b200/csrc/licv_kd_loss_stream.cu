@@ -145,6 +145,16 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// one elected lane of the (converged) warp arrives: ELECT + a predicated arrive
+__device__ __forceinline__ void warp_arrive_a(uint32_t bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}\n" ::"r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ uint4 lds128_a(uint32_t addr) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -377,10 +387,13 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
         float* row_kl = a.row_loss;
         float* row_ce = a.row_loss + a.n_rows;
         // this thread's 64 columns of tensor memory: lane quarter of the warp, column group of the warp
-        const uint32_t tcol = s_tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * (NV * 8));
-        const uint32_t ring_a = smem_u32(ring) + tid * 16, cs_a = smem_u32(cs) + tid * 16;
-        const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
+        uint32_t tcol = s_tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * (NV * 8));
+        uint32_t ring_a = smem_u32(ring) + tid * 16, cs_a = smem_u32(cs) + tid * 16;
+        uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
         const uint32_t slab_a = smem_u32(slab);
+        // opaque to the compiler from here on: it would otherwise re-derive these addresses
+        // (S2R + LEA + IMAD chains) inside the sweeps instead of keeping five registers
+        asm volatile("" : "+r"(tcol), "+r"(ring_a), "+r"(cs_a), "+r"(full_a), "+r"(empty_a));
 
         // CTA-wide sums of up to three values: warp shuffles, 16 partials through shared memory, one
         // barrier; the slabs rotate so that a fast warp's next partial never meets a slow reader
@@ -521,6 +534,7 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
             // cur: reduction 1, sweep C, reduction 2
             // ---------------------------------------------------------------------------------
             float A = 0.f, kl_row = 0.f, ce_row = 0.f, cq = 0.f;
+            float z_cur = 0.f;                           // cur: the student's partition sum
             LICV_STAMP(5);
             if (c_work) {
                 const float it_c = c_kl ? inv_t : 1.0f;
@@ -591,6 +605,7 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                     tmem_wait_st();
                     tot = cta_sum3(zs, zt, zc);
                 }
+                z_cur = tot.x;
                 // where this row's logits were: the guess for the next row's references
                 const float lz_s = lg2(tot.x);
                 const float inv_c = (c_kl ? T : 1.0f) * kLn2;             // octaves -> logit units
@@ -613,21 +628,43 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                         e0 = lds128_a(cs_a + (k * 2) * kST * 16);
                         e1 = lds128_a(cs_a + (k * 2 + 1) * kST * 16);
                     };
-                    auto c_math = [&](int k, uint32_t (&tb)[8], const uint4& e0, const uint4& e1) {
+                    // The reciprocals 1/(q+eps) are the only MUFU work of the sweep that can be shared:
+                    // 1/a and 1/b follow from ONE rcp(a b) and two products, so the four pairs of a
+                    // vector cost 2 MUFU.RCP + 9 packed products instead of 8 MUFU.RCP (3.25 instead
+                    // of 4 MUFU per element over the row; the SFU pipe is the sweep's bound).  The
+                    // product of four q+eps must stay a normal number: eps >= 1e-9 (q+eps <= 1+eps).
+                    auto c_math = [&](auto batched, int k, uint32_t (&tb)[8], const uint4& e0, const uint4& e1) {
+                        constexpr bool RCP4 = decltype(batched)::value;
                         const float2 es[4] = {as_f2(e0.x, e0.y), as_f2(e0.z, e0.w), as_f2(e1.x, e1.y),
                                               as_f2(e1.z, e1.w)};
+                        float2 q[4], p[4], qe[4], rq[4];
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            q[h] = __fmul2_rn(es[h], fs2);
+                            p[h] = __fmul2_rn(as_f2(tb[2 * h], tb[2 * h + 1]), ft2);
+                            qe[h] = __fadd2_rn(q[h], eps2);
+                        }
+                        if (RCP4) {
+                            const float2 p01 = __fmul2_rn(qe[0], qe[1]), p23 = __fmul2_rn(qe[2], qe[3]);
+                            const float2 pp = __fmul2_rn(p01, p23);
+                            const float2 r = make_float2(rcp(pp.x), rcp(pp.y));
+                            const float2 r01 = __fmul2_rn(r, p23), r23 = __fmul2_rn(r, p01);
+                            rq[0] = __fmul2_rn(r01, qe[1]);
+                            rq[1] = __fmul2_rn(r01, qe[0]);
+                            rq[2] = __fmul2_rn(r23, qe[3]);
+                            rq[3] = __fmul2_rn(r23, qe[2]);
+                        } else {
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) rq[h] = make_float2(rcp(qe[h].x), rcp(qe[h].y));
+                        }
                         float nw[8];
 #pragma unroll
                         for (int h = 0; h < 4; ++h) {
-                            const float2 q = __fmul2_rn(es[h], fs2);
-                            const float2 p = __fmul2_rn(as_f2(tb[2 * h], tb[2 * h + 1]), ft2);
-                            const float2 qe = __fadd2_rn(q, eps2);
-                            const float2 rq = make_float2(rcp(qe.x), rcp(qe.y));
-                            const float2 ratio = __fmul2_rn(__fadd2_rn(p, eps2), rq);
+                            const float2 ratio = __fmul2_rn(__fadd2_rn(p[h], eps2), rq[h]);
                             // ln(p+eps) - ln(q+eps) = ln((p+eps)/(q+eps))
                             const float2 lr = make_float2(lg2(ratio.x), lg2(ratio.y));
-                            klp2 = __ffma2_rn(p, lr, klp2);
-                            const float2 w = __fmul2_rn(__fmul2_rn(p, q), rq);
+                            klp2 = __ffma2_rn(p[h], lr, klp2);
+                            const float2 w = __fmul2_rn(__fmul2_rn(p[h], q[h]), rq[h]);
                             wp2 = __fadd2_rn(wp2, w);
                             const float2 n = __fmul2_rn(w, nkw2);
                             nw[2 * h] = n.x;
@@ -635,16 +672,24 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                         }
                         if (keep) tmem_st8(tcol + k * 8, nw);
                     };
-                    c_load(0, tbA, eA0, eA1);
+                    auto c_sweep = [&](auto batched) {
+                        c_load(0, tbA, eA0, eA1);
 #pragma unroll 1
-                    for (int k = 0; k < NV; k += 2) {
-                        tmem_ld_wait(tbA);
-                        c_load(k + 1, tbB, eB0, eB1);
-                        c_math(k, tbA, eA0, eA1);
-                        tmem_ld_wait(tbB);
-                        if (k + 2 < NV) c_load(k + 2, tbA, eA0, eA1);
-                        c_math(k + 1, tbB, eB0, eB1);
-                    }
+                        for (int k = 0; k < NV; k += 2) {
+                            tmem_ld_wait(tbA);
+                            c_load(k + 1, tbB, eB0, eB1);
+                            c_math(batched, k, tbA, eA0, eA1);
+                            tmem_ld_wait(tbB);
+                            if (k + 2 < NV) c_load(k + 2, tbA, eA0, eA1);
+                            c_math(batched, k + 1, tbB, eB0, eB1);
+                        }
+                    };
+#ifdef LICV_KD_NO_RCP4
+                    c_sweep(std::false_type{});
+#else
+                    if (eps >= 1e-9f) c_sweep(std::true_type{});
+                    else c_sweep(std::false_type{});
+#endif
                     tmem_wait_st();
                     LICV_STAMP(1);
                     const float4 r2 = cta_sum3(klp2.x + klp2.y, wp2.x + wp2.y, 0.f);
@@ -727,93 +772,102 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                                                                              : 0;
             auto fast_sweep = [&](auto mode_tag) {
                 constexpr int MODE = decltype(mode_tag)::value;
-                const float2 c2 = splat(c_row), nms = splat(-nref_s), nmt = splat(-nref_t);
-                // label relative to this thread's first element; never matches when there is none
-                int lab_rel = (c_ce && c_lab >= 0) ? c_lab - c_j0 : -1;
-                char* gk = gp + (int64_t)c_j0 * EB;
-                // vector groups [1, k_end) lie wholly inside both rows for every thread
-                const int k_end = min(c_kfull, n_kfull);
-                struct Regs {
-                    uint4 raw_s, raw_t, e0, e1;
-                    uint32_t wv[8];
-                    uint32_t ea_s;
-                };
-                Regs ra, rb;
+                static_assert(kStep == 4096, "group geometry below shifts by 12");
+                const float2 c2 = splat(MODE == 1 ? kLog2e * inv_t : kLog2e), nms = splat(-nref_s),
+                             nmt = splat(-nref_t);
+                // ---- the label's -ce_w goes into the caches ahead of the sweep (no test per vector):
+                //      MODE 1 into the -kl_w w entry in tensor memory, MODE 2 as e - Z into the e_s slot
+                //      (A = ce_w / Z there, so A (e - Z) = A e - ce_w)
+                if (c_ce && c_lab >= 0 && c_lab < V) {
+                    const int rel0 = c_lab - c_j0 + lane * EPV;           // relative to lane 0's first element
+                    if (rel0 >= 0 && (rel0 & (kStep - 1)) < 32 * EPV) {   // this warp owns the label
+                        const int kl = rel0 >> 12, el = rel0 & (EPV - 1);
+                        const bool mine = ((rel0 & (kStep - 1)) >> 3) == lane;
+                        if (MODE == 1) {
+                            uint32_t v[8];
+                            tmem_ld8_issue(tcol + kl * 8, v);
+                            tmem_ld_wait(v);
+                            float f[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                f[e] = __uint_as_float(v[e]) - ((mine && e == el) ? ce_on : 0.f);
+                            tmem_st8(tcol + kl * 8, f);
+                            tmem_wait_st();
+                        } else if (mine) {
+                            const uint32_t ad = cs_a + (uint32_t)((kl * 2 + (el >> 2)) * kST * 16 + (el & 3) * 4);
+                            float e;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(e) : "r"(ad));
+                            e -= z_cur;
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(e) : "memory");
+                        }
+                    }
+                }
+                // ---- geometry of this WARP: vector groups [k_lo, k_in) lie wholly inside both rows
+                //      (plain vector stores, no masks); the others take the edge version of the step.
+                //      Lane 0's values, broadcast: warp-uniform for the compiler too (uniform branches,
+                //      no re-convergence code around the .aligned instructions)
+                const int w0c = __shfl_sync(0xffffffffu, c_j0, 0), w0n = __shfl_sync(0xffffffffu, n_j0, 0);
+                const int k_lo = (w0c < 0 || w0n < 0) ? 1 : 0;
+                const int k_in = max(k_lo, ((V - 32 * EPV - max(w0c, w0n)) >> 12) + 1);
+                uint4 raw_s, raw_t = make_uint4(0, 0, 0, 0), e0, e1;
+                uint32_t wv[8];
+                uint32_t ea_s = 0;                   // `empty` barrier of the slot the registers came from
+                char* const g0 = gp + (int64_t)c_j0 * EB;
                 // every load of vector group k: raw logits out of the ring, the cache slots of cur.
                 // The slot's barrier was probed one step earlier (`ready`): its latency is off the path.
                 bool ready = false;
                 auto probe = [&]() { ready = mbar_test_a(full_a + slot * 8, par); };
-                auto load = [&](int k, Regs& r) {
+                auto load = [&](int k) {
                     if (MODE == 1 || (k & 1) == 0) {
                         if (!ready) mbar_wait_a(full_a + slot * 8, par);
                     }
                     const uint32_t sa = ring_a + slot * kSlotBytes;
-                    r.ea_s = empty_a + slot * 8;
+                    ea_s = empty_a + slot * 8;
                     if (MODE == 1) {
-                        r.raw_s = lds128_a(sa);
-                        r.raw_t = lds128_a(sa + kChunk);
+                        raw_s = lds128_a(sa);
+                        raw_t = lds128_a(sa + kChunk);
                         adv();
-                        tmem_ld8_issue(tcol + k * 8, r.wv);
+                        tmem_ld8_issue(tcol + k * 8, wv);
                     } else {
-                        r.raw_s = lds128_a(sa + (k & 1) * kChunk);
+                        raw_s = lds128_a(sa + (k & 1) * kChunk);
                         if (k & 1) adv();
                     }
-                    r.e0 = lds128_a(cs_a + (k * 2) * kST * 16);
-                    r.e1 = lds128_a(cs_a + (k * 2 + 1) * kST * 16);
+                    e0 = lds128_a(cs_a + (k * 2) * kST * 16);
+                    e1 = lds128_a(cs_a + (k * 2 + 1) * kST * 16);
                 };
-                auto step = [&](int k, Regs& r, Regs& rn) {
-                    const bool edge = k == 0 || k >= k_end;
+                auto step = [&](auto edge_tag, int k) {
+                    constexpr bool EDGE = decltype(edge_tag)::value;
                     if (k + 1 < NV && (MODE == 1 || (k & 1))) probe();   // the next slot's barrier
                     // ---- D(cur) -------------------------------------------------------------------------
                     float2 g[4];
                     if (MODE == 1) {
-                        tmem_ld_wait(r.wv);
-                        g[0] = __ffma2_rn(as_f2(r.e0.x, r.e0.y), A2, as_f2(r.wv[0], r.wv[1]));
-                        g[1] = __ffma2_rn(as_f2(r.e0.z, r.e0.w), A2, as_f2(r.wv[2], r.wv[3]));
-                        g[2] = __ffma2_rn(as_f2(r.e1.x, r.e1.y), A2, as_f2(r.wv[4], r.wv[5]));
-                        g[3] = __ffma2_rn(as_f2(r.e1.z, r.e1.w), A2, as_f2(r.wv[6], r.wv[7]));
+                        tmem_ld_wait(wv);
+                        g[0] = __ffma2_rn(as_f2(e0.x, e0.y), A2, as_f2(wv[0], wv[1]));
+                        g[1] = __ffma2_rn(as_f2(e0.z, e0.w), A2, as_f2(wv[2], wv[3]));
+                        g[2] = __ffma2_rn(as_f2(e1.x, e1.y), A2, as_f2(wv[4], wv[5]));
+                        g[3] = __ffma2_rn(as_f2(e1.z, e1.w), A2, as_f2(wv[6], wv[7]));
                     } else {
-                        g[0] = __fmul2_rn(as_f2(r.e0.x, r.e0.y), A2);
-                        g[1] = __fmul2_rn(as_f2(r.e0.z, r.e0.w), A2);
-                        g[2] = __fmul2_rn(as_f2(r.e1.x, r.e1.y), A2);
-                        g[3] = __fmul2_rn(as_f2(r.e1.z, r.e1.w), A2);
+                        g[0] = __fmul2_rn(as_f2(e0.x, e0.y), A2);
+                        g[1] = __fmul2_rn(as_f2(e0.z, e0.w), A2);
+                        g[2] = __fmul2_rn(as_f2(e1.x, e1.y), A2);
+                        g[3] = __fmul2_rn(as_f2(e1.z, e1.w), A2);
                     }
-                    if ((unsigned)lab_rel < (unsigned)EPV) {
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            if (lab_rel == 2 * h) g[h].x -= ce_on;
-                            if (lab_rel == 2 * h + 1) g[h].y -= ce_on;
-                        }
-                    }
-                    bool vec_store = true;
-                    if (edge) {
-                        const int jwk = c_j0 + k * kStep - lane * EPV;
-                        vec_store = jwk >= 0 && jwk + 32 * EPV <= V;
-                    }
-                    if (vec_store) {
-                        st_vec(reinterpret_cast<uint4*>(gk),
+                    if (!EDGE) {
+                        st_vec(reinterpret_cast<uint4*>(g0 + (int64_t)k * kStep * EB),
                                make_uint4(pack2<DT>(g[0]), pack2<DT>(g[1]), pack2<DT>(g[2]), pack2<DT>(g[3])));
                     } else {
                         const float gr[EPV] = {g[0].x, g[0].y, g[1].x, g[1].y, g[2].x, g[2].y, g[3].x, g[3].y};
                         store_row_vec<DT>(gp, c_j0 + k * kStep, V, true, gr);
-                    }
-                    // ---- B(nxt): raw logits out of the ring registers, slots handed back --------------
-                    if (edge) {
-                        const int jwk = n_j0 + k * kStep - lane * EPV;
-                        if (!(jwk >= 0 && jwk + 32 * EPV <= V)) {
-                            r.raw_s = mask_vec<DT>(r.raw_s, n_j0 + k * kStep, V);
-                            if (MODE == 1) r.raw_t = mask_vec<DT>(r.raw_t, n_j0 + k * kStep, V);
-                        }
+                        // ---- B(nxt): elements outside the row count as -inf
+                        raw_s = mask_vec<DT>(raw_s, n_j0 + k * kStep, V);
+                        if (MODE == 1) raw_t = mask_vec<DT>(raw_t, n_j0 + k * kStep, V);
                     }
                     float2 xs[4], xt[4];
-                    unpack2<DT>(r.raw_s, xs);
-                    if (MODE == 1) unpack2<DT>(r.raw_t, xt);
-                    if (MODE == 1 || (k & 1)) {                         // the slot may be refilled
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_a(r.ea_s);
-                    }
+                    unpack2<DT>(raw_s, xs);
+                    if (MODE == 1) unpack2<DT>(raw_t, xt);
+                    if (MODE == 1 || (k & 1)) warp_arrive_a(ea_s);          // the slot may be refilled
                     // ---- the next vector's loads, in flight under this vector's exponentials ------------
-                    if (k + 1 < NV) load(k + 1, rn);
+                    if (k + 1 < NV) load(k + 1);
                     {
                         float2 ev[4];
 #pragma unroll
@@ -837,15 +891,16 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                         }
                         tmem_st8(tcol + k * 8, ev);
                     }
-                    lab_rel -= kStep;
-                    gk += (int64_t)kStep * EB;
                 };
-                load(0, ra);
-#pragma unroll 1
-                for (int k = 0; k < NV; k += 2) {
-                    step(k, ra, rb);
-                    step(k + 1, rb, ra);
+                load(0);
+                if (k_lo) step(std::true_type{}, 0);
+                // the interior steps, unrolled: every address is a base register plus an immediate
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                    if (k >= k_lo && k < k_in) step(std::false_type{}, k);
                 }
+#pragma unroll 1
+                for (int k = k_in; k < NV; ++k) step(std::true_type{}, k);
             };
             LICV_STAMP(3);
             if (mode == 1) {

@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
     float4* const cs = reinterpret_cast<float4*>(smem);                 // [NV * 2][kST]: e_s, fp32
     unsigned char* const ring = smem + (size_t)NV * 2 * kST * 16;       // [kSlots][kSlotBytes]
     __shared__ __align__(8) uint64_t full[kMaxSlots], empty[kMaxSlots];
+    __shared__ __align__(8) uint64_t red_bar;                         // split CTA reduction: one arrival per warp
     __shared__ __align__(16) float4 slab[4][kSW];                       // reduction partials, rotating
     __shared__ uint32_t s_tmem;
     __shared__ float s_tot[2 * kSW];
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kSW);
         }
+        mbar_init(&red_bar, kSW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -447,6 +449,48 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
             }
             return make_float2(x, y);
         };
+        // The same sum in two halves with an mbarrier in place of the CTA barrier: sum2_arrive posts
+        // the warp's partials and returns at once, sum2_wait (later, after work that does not need
+        // the sums) collects all sixteen.  The waiting time at a row-wide reduction - every warp has to
+        // get there - is the largest loss of this one-row-per-SM schedule; this is how it is filled.
+        const uint32_t red_a = smem_u32(&red_bar);
+        uint32_t red_par = 0;
+        auto sum_arrive = [&](float x, float y, float z, bool three) -> uint32_t {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                x += __shfl_xor_sync(0xffffffffu, x, o);
+                y += __shfl_xor_sync(0xffffffffu, y, o);
+            }
+            if (three) {                                 // warp-uniform: a tempered KL + CE row
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+            }
+            const uint32_t base = slab_a + slab_i * (kSW * 16);
+            slab_i = (slab_i + 1) & 3u;
+            if (lane == 0) {
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(base + warp * 16), "f"(x), "f"(y),
+                             "f"(z), "f"(0.f)
+                             : "memory");
+                mbar_arrive_a(red_a);                    // release: the partial is visible to the waiters
+            }
+            return base;
+        };
+        auto sum_wait = [&](uint32_t base, bool three) -> float4 {
+            mbar_wait_a(red_a, red_par);
+            red_par ^= 1u;
+            const uint4 p = lds128_a(base + (lane & (kSW - 1)) * 16);
+            float x = __uint_as_float(p.x), y = __uint_as_float(p.y), z = __uint_as_float(p.z);
+#pragma unroll
+            for (int o = kSW / 2; o > 0; o >>= 1) {
+                x += __shfl_xor_sync(0xffffffffu, x, o);
+                y += __shfl_xor_sync(0xffffffffu, y, o);
+            }
+            if (three) {
+#pragma unroll
+                for (int o = kSW / 2; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+            }
+            return make_float4(x, y, z, 0.f);
+        };
         // Row descriptors: everything the sweeps need to know about a row is worked out ONCE, by one
         // thread per row, kDescRows rows at a time, and read back with three 16-byte loads - the
         // per-row bookkeeping (pointers, phases, flags, the label logit) executed by all 16 warps was
@@ -504,7 +548,8 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
         char* c_gp = nullptr;
         int64_t c_r = -1;
         float x_lab = 0.f;                         // cur: label logit
-        float zs = 0.f, zt = 0.f, zc = 0.f;        // cur: this thread's partition sums
+        float zs = 0.f, zt = 0.f, zc = 0.f;        // cur: this thread's partition sums (cold path)
+        uint32_t red1_base = 0;                    // cur: where reduction 1 was posted
         float ref_s = 0.f, ref_t = 0.f, ref_c = 0.f;   // cur: reference exponents of the three streams
         // where the logits of this CTA's rows live (in logit units; NaN = not known yet)
         float hint_s = __int_as_float(0x7fc00000), hint_t = hint_s;
@@ -535,12 +580,17 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
             // ---------------------------------------------------------------------------------
             float A = 0.f, kl_row = 0.f, ce_row = 0.f, cq = 0.f;
             float z_cur = 0.f;                           // cur: the student's partition sum
+            float fs = 0.f, lz_s = 0.f, tot_c = 0.f, KW = 0.f;   // 1/Z_s, lg2 Z_s, Z of the raw-logit stream, kl_w W_n
+            bool red2_pending = false;
+            uint32_t red2_base = 0;
             LICV_STAMP(5);
             if (c_work) {
                 const float it_c = c_kl ? inv_t : 1.0f;
                 const bool rnd_c = c_flags & F_RND;
                 const float c_c = rnd_c ? kLog2e : kLog2e * it_c;        // u = logit * c_c
-                float4 tot = cta_sum3(zs, zt, zc);
+                // reduction 1 was posted at the end of the sweep that built this row; the bookkeeping
+                // between the rows ran in its shadow
+                float4 tot = sum_wait(red1_base, c_cet);
                 LICV_STAMP(0);
                 const bool bad = !z_usable(tot.x) || (c_kl && !z_usable(tot.y)) || (c_cet && !z_usable(tot.z));
                 if (bad) {
@@ -607,16 +657,16 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                 }
                 z_cur = tot.x;
                 // where this row's logits were: the guess for the next row's references
-                const float lz_s = lg2(tot.x);
+                lz_s = lg2(tot.x);
+                tot_c = tot.z;
                 const float inv_c = (c_kl ? T : 1.0f) * kLn2;             // octaves -> logit units
                 hint_s = (ref_s + lz_s) * inv_c;
                 if (c_kl) hint_t = (ref_t + lg2(tot.y)) * inv_c;
-                const float fs = rcp(tot.x);                              // q = e_s * fs
-                float W = 0.f;
+                fs = rcp(tot.x);                                          // q = e_s * fs
                 if (c_kl) {
                     // ---- sweep C: KL terms and w; -kl_w w replaces e_t in tensor memory ------------
                     const float ft = rcp(tot.y);                          // p = e_t * ft
-                    const float2 fs2 = splat(fs), ft2 = splat(ft), eps2 = splat(eps), nkw2 = splat(-kl_w);
+                    const float2 fs2 = splat(fs), ft2 = splat(ft), eps2 = splat(eps), fsn2 = splat(-kl_w * fs);
                     float2 klp2 = splat(0.f), wp2 = splat(0.f);
                     const bool keep = a.dstu != nullptr;
                     // software pipeline: the cache reads of vector k+1 are in flight under the
@@ -637,12 +687,14 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                         constexpr bool RCP4 = decltype(batched)::value;
                         const float2 es[4] = {as_f2(e0.x, e0.y), as_f2(e0.z, e0.w), as_f2(e1.x, e1.y),
                                               as_f2(e1.z, e1.w)};
-                        float2 q[4], p[4], qe[4], rq[4];
+                        // 10.25 fp32 operations per element (the fp32 pipe is this sweep's second bound):
+                        // q itself is never formed - q+eps by one FMA, and w only as -kl_w w = t (e_s fsn)
+                        // with t = p/(q+eps), which also gives the ratio (p+eps)/(q+eps) = t + eps/(q+eps)
+                        float2 p[4], qe[4], rq[4];
 #pragma unroll
                         for (int h = 0; h < 4; ++h) {
-                            q[h] = __fmul2_rn(es[h], fs2);
                             p[h] = __fmul2_rn(as_f2(tb[2 * h], tb[2 * h + 1]), ft2);
-                            qe[h] = __fadd2_rn(q[h], eps2);
+                            qe[h] = __ffma2_rn(es[h], fs2, eps2);
                         }
                         if (RCP4) {
                             const float2 p01 = __fmul2_rn(qe[0], qe[1]), p23 = __fmul2_rn(qe[2], qe[3]);
@@ -660,13 +712,13 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                         float nw[8];
 #pragma unroll
                         for (int h = 0; h < 4; ++h) {
-                            const float2 ratio = __fmul2_rn(__fadd2_rn(p[h], eps2), rq[h]);
+                            const float2 t = __fmul2_rn(p[h], rq[h]);
+                            const float2 ratio = __ffma2_rn(eps2, rq[h], t);
                             // ln(p+eps) - ln(q+eps) = ln((p+eps)/(q+eps))
                             const float2 lr = make_float2(lg2(ratio.x), lg2(ratio.y));
                             klp2 = __ffma2_rn(p[h], lr, klp2);
-                            const float2 w = __fmul2_rn(__fmul2_rn(p[h], q[h]), rq[h]);
-                            wp2 = __fadd2_rn(wp2, w);
-                            const float2 n = __fmul2_rn(w, nkw2);
+                            const float2 n = __fmul2_rn(t, __fmul2_rn(es[h], fsn2));   // -kl_w p q/(q+eps)
+                            wp2 = __fadd2_rn(wp2, n);
                             nw[2 * h] = n.x;
                             nw[2 * h + 1] = n.y;
                         }
@@ -692,25 +744,35 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
 #endif
                     tmem_wait_st();
                     LICV_STAMP(1);
-                    const float4 r2 = cta_sum3(klp2.x + klp2.y, wp2.x + wp2.y, 0.f);
+                    // reduction 2 is split: the partials are posted here, the sums are read in
+                    // finish_cur - a fast sweep runs the next row's first exponentials in between
+                    red2_base = sum_arrive(klp2.x + klp2.y, wp2.x + wp2.y, 0.f, false);
+                    red2_pending = true;
+                }
+            }
+            // cur's second reduction (if one is pending), the gradient's row factor A, the CE term
+            auto finish_cur = [&]() {
+                if (!c_work) return;
+                if (red2_pending) {
+                    const float4 r2 = sum_wait(red2_base, false);
                     LICV_STAMP(2);
                     kl_row = r2.x * kLn2;
-                    W = r2.y;
+                    KW = -r2.y;                                          // the sweep summed -kl_w w
                 }
                 const float ce_on = c_ce ? ce_w : 0.f;
                 if (c_cet) {
-                    A = fs * kl_w * W;
-                    cq = ce_on * rcp(tot.z);                            // ce_w softmax(x) = 2^(u - ref_c) cq
+                    A = fs * KW;
+                    cq = ce_on * rcp(tot_c);                            // ce_w softmax(x) = 2^(u - ref_c) cq
                 } else {
-                    A = fs * fmaf(kl_w, W, ce_on);                      // c_kl false: W = 0 -> fs * ce_w
+                    A = fs * (KW + ce_on);                              // c_kl false: KW = 0 -> fs * ce_w
                 }
                 if (tid == 0 && c_ce) {
                     const bool lab_ok = c_lab >= 0 && c_lab < V;
                     // an out-of-range label is an error in torch; poison the loss instead
-                    const float lse = c_cet ? (ref_c + lg2(tot.z)) * kLn2 : (ref_s + lz_s) * kLn2;
+                    const float lse = c_cet ? (ref_c + lg2(tot_c)) * kLn2 : (ref_s + lz_s) * kLn2;
                     ce_row = lab_ok ? lse - x_lab : __int_as_float(0x7fc00000);
                 }
-            }
+            };
 
             if (!c_valid && !n_valid) break;
 
@@ -720,7 +782,7 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
             // ---------------------------------------------------------------------------------
             char* const gp = c_gp;
             const bool g_vec = c_flags & F_GVEC;
-            const float2 A2 = splat(A);
+            float2 A2 = splat(0.f);              // set once finish_cur has run
             const float ce_on = c_ce ? ce_w : 0.f;
             const float mc_cur = ref_c;          // cur's raw-logit reference (D of a tempered KL + CE row)
 
@@ -770,11 +832,60 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
             const int mode = (d_fast && b_plain && c_kl && nx_kl && n_d == 0) ? 1
                              : (d_fast && b_plain && !c_kl && !nx_kl)        ? 2
                                                                              : 0;
-            auto fast_sweep = [&](auto mode_tag) {
+            // EARLY (MODE 1): the exponentials of nxt's first vector group are computed, into
+            // registers, BEFORE cur's second reduction is collected (finish_cur) - 32 MUFU per thread
+            // that run while the slowest warp is still on its way to the reduction.
+            auto fast_sweep = [&](auto mode_tag, auto early_tag) {
                 constexpr int MODE = decltype(mode_tag)::value;
+                constexpr bool EARLY = decltype(early_tag)::value;
                 static_assert(kStep == 4096, "group geometry below shifts by 12");
+                static_assert(!EARLY || MODE == 1, "the early group is written for KL rows");
                 const float2 c2 = splat(MODE == 1 ? kLog2e * inv_t : kLog2e), nms = splat(-nref_s),
                              nmt = splat(-nref_t);
+                // ---- geometry of this WARP: vector groups [k_lo, k_in) lie wholly inside both rows
+                //      (plain vector stores, no masks); the others take the edge version of the step.
+                //      Lane 0's values, broadcast: warp-uniform for the compiler too (uniform branches,
+                //      no re-convergence code around the .aligned instructions)
+                const int w0c = __shfl_sync(0xffffffffu, c_j0, 0), w0n = __shfl_sync(0xffffffffu, n_j0, 0);
+                const int k_lo = (w0c < 0 || w0n < 0) ? 1 : 0;
+                const int k_in = max(k_lo, ((V - 32 * EPV - max(w0c, w0n)) >> 12) + 1);
+                uint4 raw_s, raw_t = make_uint4(0, 0, 0, 0), e0, e1;
+                uint32_t wv[8];
+                uint32_t ea_s = 0;                   // `empty` barrier of the slot the registers came from
+                float2 ev0s[4];                      // EARLY: nxt's group 0, waiting for its cache slots
+                float ev0t[8];
+                if (EARLY) {
+                    mbar_wait_a(full_a + slot * 8, par);
+                    const uint32_t sa = ring_a + slot * kSlotBytes;
+                    ea_s = empty_a + slot * 8;
+                    raw_s = lds128_a(sa);
+                    raw_t = lds128_a(sa + kChunk);
+                    adv();
+                    if (k_lo) {
+                        raw_s = mask_vec<DT>(raw_s, n_j0, V);
+                        raw_t = mask_vec<DT>(raw_t, n_j0, V);
+                    }
+                    float2 xs[4], xt[4];
+                    unpack2<DT>(raw_s, xs);
+                    unpack2<DT>(raw_t, xt);
+                    warp_arrive_a(ea_s);
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const float2 u = __ffma2_rn(xs[h], c2, nms);
+                        ev0s[h] = make_float2(ex2(u.x), ex2(u.y));
+                        zs2 = __fadd2_rn(zs2, ev0s[h]);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const float2 u = __ffma2_rn(xt[h], c2, nmt);
+                        const float2 e = make_float2(ex2(u.x), ex2(u.y));
+                        zt2 = __fadd2_rn(zt2, e);
+                        ev0t[2 * h] = e.x;
+                        ev0t[2 * h + 1] = e.y;
+                    }
+                    finish_cur();
+                    A2 = splat(A);
+                }
                 // ---- the label's -ce_w goes into the caches ahead of the sweep (no test per vector):
                 //      MODE 1 into the -kl_w w entry in tensor memory, MODE 2 as e - Z into the e_s slot
                 //      (A = ce_w / Z there, so A (e - Z) = A e - ce_w)
@@ -802,16 +913,6 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                         }
                     }
                 }
-                // ---- geometry of this WARP: vector groups [k_lo, k_in) lie wholly inside both rows
-                //      (plain vector stores, no masks); the others take the edge version of the step.
-                //      Lane 0's values, broadcast: warp-uniform for the compiler too (uniform branches,
-                //      no re-convergence code around the .aligned instructions)
-                const int w0c = __shfl_sync(0xffffffffu, c_j0, 0), w0n = __shfl_sync(0xffffffffu, n_j0, 0);
-                const int k_lo = (w0c < 0 || w0n < 0) ? 1 : 0;
-                const int k_in = max(k_lo, ((V - 32 * EPV - max(w0c, w0n)) >> 12) + 1);
-                uint4 raw_s, raw_t = make_uint4(0, 0, 0, 0), e0, e1;
-                uint32_t wv[8];
-                uint32_t ea_s = 0;                   // `empty` barrier of the slot the registers came from
                 char* const g0 = gp + (int64_t)c_j0 * EB;
                 // every load of vector group k: raw logits out of the ring, the cache slots of cur.
                 // The slot's barrier was probed one step earlier (`ready`): its latency is off the path.
@@ -892,22 +993,51 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                         tmem_st8(tcol + k * 8, ev);
                     }
                 };
-                load(0);
-                if (k_lo) step(std::true_type{}, 0);
+                if (EARLY) {
+                    // group 0: the gradient out of cur's cache slots, then nxt's exponentials into them
+                    tmem_ld8_issue(tcol, wv);
+                    e0 = lds128_a(cs_a);
+                    e1 = lds128_a(cs_a + kST * 16);
+                    probe();
+                    tmem_ld_wait(wv);
+                    float2 g[4];
+                    g[0] = __ffma2_rn(as_f2(e0.x, e0.y), A2, as_f2(wv[0], wv[1]));
+                    g[1] = __ffma2_rn(as_f2(e0.z, e0.w), A2, as_f2(wv[2], wv[3]));
+                    g[2] = __ffma2_rn(as_f2(e1.x, e1.y), A2, as_f2(wv[4], wv[5]));
+                    g[3] = __ffma2_rn(as_f2(e1.z, e1.w), A2, as_f2(wv[6], wv[7]));
+                    if (!k_lo) {
+                        st_vec(reinterpret_cast<uint4*>(g0),
+                               make_uint4(pack2<DT>(g[0]), pack2<DT>(g[1]), pack2<DT>(g[2]), pack2<DT>(g[3])));
+                    } else {
+                        const float gr[EPV] = {g[0].x, g[0].y, g[1].x, g[1].y, g[2].x, g[2].y, g[3].x, g[3].y};
+                        store_row_vec<DT>(gp, c_j0, V, true, gr);
+                    }
+                    load(1);
+                    sts128_a(cs_a, ev0s[0], ev0s[1]);
+                    sts128_a(cs_a + kST * 16, ev0s[2], ev0s[3]);
+                    tmem_st8(tcol, ev0t);
+                } else {
+                    load(0);
+                    if (k_lo) step(std::true_type{}, 0);
+                }
                 // the interior steps, unrolled: every address is a base register plus an immediate
 #pragma unroll
-                for (int k = 0; k < NV; ++k) {
+                for (int k = EARLY ? 1 : 0; k < NV; ++k) {
                     if (k >= k_lo && k < k_in) step(std::false_type{}, k);
                 }
 #pragma unroll 1
-                for (int k = k_in; k < NV; ++k) step(std::true_type{}, k);
+                for (int k = EARLY ? max(k_in, 1) : k_in; k < NV; ++k) step(std::true_type{}, k);
             };
             LICV_STAMP(3);
             if (mode == 1) {
-                fast_sweep(std::integral_constant<int, 1>{});
+                fast_sweep(std::integral_constant<int, 1>{}, std::true_type{});     // runs finish_cur itself
             } else if (mode == 2) {
-                fast_sweep(std::integral_constant<int, 2>{});
+                finish_cur();
+                A2 = splat(A);
+                fast_sweep(std::integral_constant<int, 2>{}, std::false_type{});
             } else {
+                finish_cur();
+                A2 = splat(A);
 #pragma unroll 1
                 for (int k = 0; k < NV; ++k) {
                     // ---- issue every load of this vector first -----------------------------------------
@@ -1049,6 +1179,8 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                     }
                 }
             }
+            // nxt's reduction 1: post the partition sums now, collect them at the top of the next pass
+            if (n_work) red1_base = sum_arrive(zs2.x + zs2.y, zt2.x + zt2.y, zc2.x + zc2.y, n_cet);
             if (nx_kl) tmem_wait_st();
             LICV_STAMP(4);
 #ifdef LICV_TRACE

@@ -250,6 +250,48 @@ def test_kd_loss_full_size_properties(ops):
     assert np.isfinite(float(losses[2]))
 
 
+@pytest.mark.parametrize("dt,V", [("bf16", 32002), ("fp16", 32003)])
+def test_kd_loss_several_rows_per_sm_every_sweep_kind(ops, dt, V):
+    """600 rows = four per SM: the stream kernel's fused sweeps between neighbouring rows of one SM
+    run in all their kinds - KL row after KL row (rows r, r+148, r+296 of the first 400), a CE-only
+    row after a KL row, CE-only after CE-only, rows in no loss in between - with labels on the
+    first / last element of a row and on both sides of the 4096-element group boundaries.  The
+    whole gradient and the losses against the oracle."""
+    rng = np.random.default_rng(600 + V)
+    R = 600
+    stu_np = rng.normal(size=(R, V)) * 3
+    tea_np = stu_np[:400] + rng.normal(size=(400, V))
+    ktr = np.full(R, -1, np.int32)
+    ktr[:400] = np.arange(400, dtype=np.int32)
+    lab = rng.integers(0, V, size=R).astype(np.int64)
+    lab[0:8] = [0, 1, 7, 8, 4095, 4096, V - 1, V - 2]
+    lab[148:152] = [4088, 4089, 28671, 28672]
+    lab[450:454] = [0, V - 1, 4096, 8191]
+    lab[500:520:3] = -100                   # CE-only rows without a label: rows in no loss
+    lab[30:40:2] = -100                     # KL rows without CE
+    stu = dev(stu_np, TD[dt])
+    tea = dev(tea_np, TD[dt])
+    want = O.kd_loss_rows(host(stu), host(tea), ktr, lab, 1.0, 1e-6, 0.5, logit_fmt=dt)
+    # means over 400 / 600 rows put most fp16 gradient elements among the subnormals: a loss scale,
+    # as fp16 training uses one, keeps the comparison about the kernel and not about the format
+    scale = 4096.0 if dt == "fp16" else 1.0
+    for in_place in (False, True):
+        losses, dstu = ops.kd_loss_raw(stu.clone(), tea, torch.tensor(ktr).cuda(), torch.tensor(lab).cuda(),
+                                       None, want["N"], want["M"], 1.0, 1e-6, 0.5, grad_scale=scale,
+                                       in_place=in_place)
+        kl, ce, tot = [float(x) for x in losses]
+        assert abs(kl - want["kl"]) <= 1e-5 * abs(want["kl"]) + 1e-7
+        assert abs(ce - want["ce"]) <= 1e-5 * abs(want["ce"]) + 1e-7
+        assert abs(tot - want["loss"]) <= 1e-5 * abs(want["loss"]) + 1e-7
+        got = host(dstu) / scale
+        assert rel_err(got, want["d_stu"]) < 1.2 * EPS[dt]
+        # row by row as well: one wrong row would drown in the norm of 600
+        for r in (0, 5, 147, 148, 151, 296, 399, 400, 450, 453, 599):
+            assert rel_err(got[r], want["d_stu"][r]) < 1.5 * EPS[dt], r
+        dead = (ktr < 0) & (lab == -100)
+        assert dead.any() and not got[dead].any()
+
+
 def test_kd_loss_far_from_first_vector_and_minus_inf(ops):
     """Rows whose large logits sit far (in octaves) above what a thread sees first: the stream
     kernel takes its exponentials relative to the thread's first vector and must rebuild such a

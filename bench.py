@@ -667,7 +667,11 @@ def run_e2e_host(hp, steps, warmup, seed):
         v.mul_(0.999).addcmul_(g, g, value=0.001)
         p.addcdiv_(m, (v.sqrt() / (1.0 - 0.999 ** t) ** 0.5).add_(1e-8), value=-lr / (1.0 - 0.9 ** t))
 
+    seg = [0.0, 0.0, 0.0, 0.0]    # LICV_E2E_SEGMENTS=1: host prologue / call issue / drain / host optimizer
+    want_seg = env_int("LICV_E2E_SEGMENTS", 0) != 0
+
     def step():
+        t_a = time.perf_counter()
         # a1 + a2: the product that crosses into the hooks; a6 + a7 + a9: row pairing and labels
         torch.mul(alpha.unsqueeze(-1), vec, out=icv_h)
         ktr.fill_(-1)
@@ -675,6 +679,7 @@ def run_e2e_host(hp, steps, warmup, seed):
         lab.fill_(-100)
         lab.view(B, T)[:, :T - 1] = ids[:, 1:]
         n_kl, n_ce = B * T4, B * (T - 1)
+        t_b = time.perf_counter()
         for l in range(L):
             # the forward keeps h on the device for its backward (saved-for-backward), so the
             # backward moves only g in and dh out
@@ -691,7 +696,9 @@ def run_e2e_host(hp, steps, warmup, seed):
                                                         icv_h[l].data_ptr(), dh_h[l].data_ptr(),
                                                         ds_h[l].data_ptr(), n_tok, d, hp.code,
                                                         hp.code, hp.flags), "inject_bwd_host_saved")
+        t_c = time.perf_counter()
         hp.abi.check(lib.licv_host_sync(sess), "host_sync")
+        t_d = time.perf_counter()
         # autograd of a2, then f2: global-norm clip + AdamW with the two learning rates
         d_vec = alpha.unsqueeze(-1) * ds_h
         d_alpha = (ds_h * vec).sum(1)
@@ -700,14 +707,22 @@ def run_e2e_host(hp, steps, warmup, seed):
         step_no[0] += 1
         adamw(vec, d_vec, m_v, v_v, 1e-4, coef, step_no[0])
         adamw(alpha, d_alpha, m_a, v_a, 1e-2, coef, step_no[0])
+        if want_seg:
+            t_e = time.perf_counter()
+            for i, v in enumerate((t_b - t_a, t_c - t_b, t_d - t_c, t_e - t_d)):
+                seg[i] += v
         return float(loss_h[2])   # the device->host read of the step's result
 
     for _ in range(warmup):
         step()
+    seg[:] = [0.0, 0.0, 0.0, 0.0]
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
+    if want_seg:
+        print("e2e segments ms/step: prologue %.3f issue %.3f drain %.3f optimizer %.3f of %.3f" %
+              tuple([1e3 * v / steps for v in seg] + [1e3 * dt]), file=sys.stderr, flush=True)
     lib.licv_host_session_destroy(sess)
     # bytes that actually cross the link per step: h (once) and g per layer, the shift twice,
     # student + teacher logits, the two row lists; back: out and dh per layer, d_shift, d(logits)

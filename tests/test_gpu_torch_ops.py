@@ -36,8 +36,10 @@ def test_registered_inject_equals_autograd_function(T):
         out = fn(a, b)
         out.backward(up)
         outs.append((out.detach(), a.grad, b.grad))
-    for x, y in zip(*outs):
-        assert torch.equal(x, y)
+    (o0, dh0, ds0), (o1, dh1, ds1) = outs
+    assert torch.equal(o0, o1) and torch.equal(dh0, dh1)
+    # d_shift is accumulated with fp32 atomics: equal up to the order of the additions
+    assert float((ds0 - ds1).abs().max()) <= 1e-5 * float(ds0.abs().max())
 
 
 def test_registered_kd_loss_equals_raw_kernel(T):

@@ -54,6 +54,10 @@ constexpr int kMaxSlots = 16;
 constexpr int kPeekMargin = 8;             // octaves added to the maximum of a row's first vector group
 constexpr int kDescRows = 16;             // row descriptors staged in shared memory at a time (power of two)
 constexpr int kSmemBudget = 230400;       // dynamic shared memory (static part: ~1.6 KB)
+// probes before a wait gives up (a broken pipeline traps - the launch fails - instead of hanging the
+// GPU).  A probe returns after ~0.1 us or more; the longest legitimate wait is a few us (a typical
+// one: 30 probes), so this is 4000 times the typical wait and still bounded (about two minutes at the longest)
+constexpr int kSpinLimit = 1 << 17;
 
 __host__ __device__ constexpr int stream_slots(int nv) {
     return (kSmemBudget - nv * 2 * kST * 16) / kSlotBytes > kMaxSlots
@@ -88,7 +92,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
     if (mbar_try(bar, parity)) return;
     int spins = 0;
     while (!mbar_try(bar, parity)) {
-        if (++spins > 8000) __trap();
+        if (++spins > kSpinLimit) __trap();
     }
 }
 // 1-D TMA bulk copy global -> shared, completing on an mbarrier.  No L2 cache hint: evict-first
@@ -139,7 +143,7 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
     if (mbar_try_a(bar, parity)) return;
     int spins = 0;
     while (!mbar_try_a(bar, parity)) {
-        if (++spins > 8000) __trap();
+        if (++spins > kSpinLimit) __trap();
     }
 }
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {

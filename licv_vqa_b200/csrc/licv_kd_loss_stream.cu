@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                 if (c_kl) {
                     // ---- sweep C: KL terms and w; -kl_w w replaces e_t in tensor memory ------------
                     const float ft = rcp(tot.y);                          // p = e_t * ft
-                    const float2 fs2 = splat(fs), ft2 = splat(ft), eps2 = splat(eps), fsn2 = splat(-kl_w * fs);
+                    const float2 fs2 = splat(fs), ft2 = splat(ft), eps2 = splat(eps);
                     float2 klp2 = splat(0.f), wp2 = splat(0.f);
                     const bool keep = a.dstu != nullptr;
                     // software pipeline: the cache reads of vector k+1 are in flight under the
@@ -691,9 +691,10 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                         constexpr bool RCP4 = decltype(batched)::value;
                         const float2 es[4] = {as_f2(e0.x, e0.y), as_f2(e0.z, e0.w), as_f2(e1.x, e1.y),
                                               as_f2(e1.z, e1.w)};
-                        // 10.25 fp32 operations per element (the fp32 pipe is this sweep's second bound):
-                        // q itself is never formed - q+eps by one FMA, and w only as -kl_w w = t (e_s fsn)
-                        // with t = p/(q+eps), which also gives the ratio (p+eps)/(q+eps) = t + eps/(q+eps)
+                        // 8.25 fp32 operations per element (the fp32 pipe is this sweep's second bound): q
+                        // itself is never formed - q+eps by one FMA - and of w only t = p/(q+eps) is kept:
+                        // it gives the ratio (p+eps)/(q+eps) = t + eps/(q+eps), W_n = sum p - eps sum t
+                        // (p q/(q+eps) = p - eps t), and sweep D forms e_s (A - kl_w fs t) from it
                         float2 p[4], qe[4], rq[4];
 #pragma unroll
                         for (int h = 0; h < 4; ++h) {
@@ -721,10 +722,9 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                             // ln(p+eps) - ln(q+eps) = ln((p+eps)/(q+eps))
                             const float2 lr = make_float2(lg2(ratio.x), lg2(ratio.y));
                             klp2 = __ffma2_rn(p[h], lr, klp2);
-                            const float2 n = __fmul2_rn(t, __fmul2_rn(es[h], fsn2));   // -kl_w p q/(q+eps)
-                            wp2 = __fadd2_rn(wp2, n);
-                            nw[2 * h] = n.x;
-                            nw[2 * h + 1] = n.y;
+                            wp2 = __fadd2_rn(wp2, t);
+                            nw[2 * h] = t.x;
+                            nw[2 * h + 1] = t.y;
                         }
                         if (keep) tmem_st8(tcol + k * 8, nw);
                     };
@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                     const float4 r2 = sum_wait(red2_base, false);
                     LICV_STAMP(2);
                     kl_row = r2.x * kLn2;
-                    KW = -r2.y;                                          // the sweep summed -kl_w w
+                    KW = kl_w * (1.0f - eps * r2.y);                     // W_n = sum p - eps sum t, sum p = 1
                 }
                 const float ce_on = c_ce ? ce_w : 0.f;
                 if (c_cet) {
@@ -786,7 +786,7 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
             // ---------------------------------------------------------------------------------
             char* const gp = c_gp;
             const bool g_vec = c_flags & F_GVEC;
-            float2 A2 = splat(0.f);              // set once finish_cur has run
+            float2 A2 = splat(0.f), F2 = splat(0.f);   // A and -kl_w / Z_s, set once finish_cur has run
             const float ce_on = c_ce ? ce_w : 0.f;
             const float mc_cur = ref_c;          // cur's raw-logit reference (D of a tempered KL + CE row)
 
@@ -888,8 +888,10 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                         ev0t[2 * h + 1] = e.y;
                     }
                     finish_cur();
-                    A2 = splat(A);
+                    A2 = splat(A), F2 = splat(-kl_w * fs);
                 }
+                float lab_val = 0.f;
+                bool lab_mine = false;
                 // ---- the label's -ce_w goes into the caches ahead of the sweep (no test per vector):
                 //      MODE 1 into the -kl_w w entry in tensor memory, MODE 2 as e - Z into the e_s slot
                 //      (A = ce_w / Z there, so A (e - Z) = A e - ce_w)
@@ -899,15 +901,19 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                         const int kl = rel0 >> 12, el = rel0 & (EPV - 1);
                         const bool mine = ((rel0 & (kStep - 1)) >> 3) == lane;
                         if (MODE == 1) {
+                            // g[label] = e (A - kl_w fs t) - ce_w in fp32, kept by its owner and stored
+                            // over the vector store of the sweep (same thread: ordered)
                             uint32_t v[8];
                             tmem_ld8_issue(tcol + kl * 8, v);
+                            const uint32_t ad = cs_a + (uint32_t)((kl * 2 + (el >> 2)) * kST * 16 + (el & 3) * 4);
+                            float e;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(e) : "r"(ad));
                             tmem_ld_wait(v);
-                            float f[8];
+                            float tl = 0.f;
 #pragma unroll
-                            for (int e = 0; e < 8; ++e)
-                                f[e] = __uint_as_float(v[e]) - ((mine && e == el) ? ce_on : 0.f);
-                            tmem_st8(tcol + kl * 8, f);
-                            tmem_wait_st();
+                            for (int i = 0; i < 8; ++i) tl = (i == el) ? __uint_as_float(v[i]) : tl;
+                            lab_val = fmaf(e, fmaf(tl, F2.x, A2.x), -ce_on);
+                            lab_mine = mine;
                         } else if (mine) {
                             const uint32_t ad = cs_a + (uint32_t)((kl * 2 + (el >> 2)) * kST * 16 + (el & 3) * 4);
                             float e;
@@ -947,10 +953,10 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                     float2 g[4];
                     if (MODE == 1) {
                         tmem_ld_wait(wv);
-                        g[0] = __ffma2_rn(as_f2(e0.x, e0.y), A2, as_f2(wv[0], wv[1]));
-                        g[1] = __ffma2_rn(as_f2(e0.z, e0.w), A2, as_f2(wv[2], wv[3]));
-                        g[2] = __ffma2_rn(as_f2(e1.x, e1.y), A2, as_f2(wv[4], wv[5]));
-                        g[3] = __ffma2_rn(as_f2(e1.z, e1.w), A2, as_f2(wv[6], wv[7]));
+                        g[0] = __fmul2_rn(as_f2(e0.x, e0.y), __ffma2_rn(as_f2(wv[0], wv[1]), F2, A2));
+                        g[1] = __fmul2_rn(as_f2(e0.z, e0.w), __ffma2_rn(as_f2(wv[2], wv[3]), F2, A2));
+                        g[2] = __fmul2_rn(as_f2(e1.x, e1.y), __ffma2_rn(as_f2(wv[4], wv[5]), F2, A2));
+                        g[3] = __fmul2_rn(as_f2(e1.z, e1.w), __ffma2_rn(as_f2(wv[6], wv[7]), F2, A2));
                     } else {
                         g[0] = __fmul2_rn(as_f2(e0.x, e0.y), A2);
                         g[1] = __fmul2_rn(as_f2(e0.z, e0.w), A2);
@@ -1005,10 +1011,10 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                     probe();
                     tmem_ld_wait(wv);
                     float2 g[4];
-                    g[0] = __ffma2_rn(as_f2(e0.x, e0.y), A2, as_f2(wv[0], wv[1]));
-                    g[1] = __ffma2_rn(as_f2(e0.z, e0.w), A2, as_f2(wv[2], wv[3]));
-                    g[2] = __ffma2_rn(as_f2(e1.x, e1.y), A2, as_f2(wv[4], wv[5]));
-                    g[3] = __ffma2_rn(as_f2(e1.z, e1.w), A2, as_f2(wv[6], wv[7]));
+                    g[0] = __fmul2_rn(as_f2(e0.x, e0.y), __ffma2_rn(as_f2(wv[0], wv[1]), F2, A2));
+                    g[1] = __fmul2_rn(as_f2(e0.z, e0.w), __ffma2_rn(as_f2(wv[2], wv[3]), F2, A2));
+                    g[2] = __fmul2_rn(as_f2(e1.x, e1.y), __ffma2_rn(as_f2(wv[4], wv[5]), F2, A2));
+                    g[3] = __fmul2_rn(as_f2(e1.z, e1.w), __ffma2_rn(as_f2(wv[6], wv[7]), F2, A2));
                     if (!k_lo) {
                         st_vec(reinterpret_cast<uint4*>(g0),
                                make_uint4(pack2<DT>(g[0]), pack2<DT>(g[1]), pack2<DT>(g[2]), pack2<DT>(g[3])));
@@ -1031,17 +1037,18 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                 }
 #pragma unroll 1
                 for (int k = EARLY ? max(k_in, 1) : k_in; k < NV; ++k) step(std::true_type{}, k);
+                if (MODE == 1 && lab_mine) store_elem<DT>(gp, c_lab, lab_val);
             };
             LICV_STAMP(3);
             if (mode == 1) {
                 fast_sweep(std::integral_constant<int, 1>{}, std::true_type{});     // runs finish_cur itself
             } else if (mode == 2) {
                 finish_cur();
-                A2 = splat(A);
+                A2 = splat(A), F2 = splat(-kl_w * fs);
                 fast_sweep(std::integral_constant<int, 2>{}, std::false_type{});
             } else {
                 finish_cur();
-                A2 = splat(A);
+                A2 = splat(A), F2 = splat(-kl_w * fs);
 #pragma unroll 1
                 for (int k = 0; k < NV; ++k) {
                     // ---- issue every load of this vector first -----------------------------------------
@@ -1079,10 +1086,10 @@ __global__ void __launch_bounds__(kBlock, 1) kd_loss_stream_kernel(KdArgs a) {
                         float2 g[4];
                         if (d_grad) {
                             if (c_kl) tmem_ld_wait(wv);
-                            g[0] = __ffma2_rn(make_float2(e0.x, e0.y), A2, as_f2(wv[0], wv[1]));
-                            g[1] = __ffma2_rn(make_float2(e0.z, e0.w), A2, as_f2(wv[2], wv[3]));
-                            g[2] = __ffma2_rn(make_float2(e1.x, e1.y), A2, as_f2(wv[4], wv[5]));
-                            g[3] = __ffma2_rn(make_float2(e1.z, e1.w), A2, as_f2(wv[6], wv[7]));
+                            g[0] = __fmul2_rn(make_float2(e0.x, e0.y), __ffma2_rn(as_f2(wv[0], wv[1]), F2, A2));
+                            g[1] = __fmul2_rn(make_float2(e0.z, e0.w), __ffma2_rn(as_f2(wv[2], wv[3]), F2, A2));
+                            g[2] = __fmul2_rn(make_float2(e1.x, e1.y), __ffma2_rn(as_f2(wv[4], wv[5]), F2, A2));
+                            g[3] = __fmul2_rn(make_float2(e1.z, e1.w), __ffma2_rn(as_f2(wv[6], wv[7]), F2, A2));
                             if (c_cet) {
                                 // CE on the raw logits of a tempered KL row: the row is read once more
                                 uint4 v[1];

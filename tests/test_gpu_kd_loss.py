@@ -292,6 +292,26 @@ def test_kd_loss_several_rows_per_sm_every_sweep_kind(ops, dt, V):
         assert dead.any() and not got[dead].any()
 
 
+@pytest.mark.parametrize("eps", [1e-10, 1e-4])
+def test_kd_loss_other_kl_eps(ops, eps):
+    """kl_eps is an option (icv_module.py:121-134).  The stream kernel shares one reciprocal among
+    four q+eps only while their product stays a normal number (eps >= 1e-9): a smaller eps takes the
+    plain reciprocals, a larger one the shared ones with other magnitudes.  300 rows: two per SM."""
+    rng = np.random.default_rng(77)
+    R, V = 300, 32002
+    stu_np = rng.normal(size=(R, V)) * 3
+    tea_np = stu_np + rng.normal(size=(R, V))
+    ktr = np.arange(R, dtype=np.int32)
+    lab = rng.integers(0, V, size=R).astype(np.int64)
+    stu, tea = dev(stu_np, torch.bfloat16), dev(tea_np, torch.bfloat16)
+    want = O.kd_loss_rows(host(stu), host(tea), ktr, lab, 1.0, eps, 0.5, logit_fmt="bf16")
+    losses, dstu = ops.kd_loss_raw(stu.clone(), tea, torch.tensor(ktr).cuda(), torch.tensor(lab).cuda(), None,
+                                   want["N"], want["M"], 1.0, eps, 0.5, in_place=False)
+    assert abs(float(losses[0]) - want["kl"]) <= 1e-5 * abs(want["kl"]) + 1e-7
+    assert abs(float(losses[2]) - want["loss"]) <= 1e-5 * abs(want["loss"]) + 1e-7
+    assert rel_err(host(dstu), want["d_stu"]) < 1.2 * EPS["bf16"]
+
+
 def test_kd_loss_far_from_first_vector_and_minus_inf(ops):
     """Rows whose large logits sit far (in octaves) above what a thread sees first: the stream
     kernel takes its exponentials relative to the thread's first vector and must rebuild such a

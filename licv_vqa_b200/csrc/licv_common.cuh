@@ -218,6 +218,16 @@ struct GridCapScope {
 // global memory.  `pdl_launch_dependents()` lets the NEXT kernel begin its own prologue.  At the
 // training shape (2-6 MB per launch) the gaps between launches are a third of the step.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// L2 prefetch hints.  They may run BEFORE pdl_wait(): a prefetch observes no value (L2 is the point
+// of coherence - a line the previous kernel writes afterwards is simply updated in place), so at
+// the latency-bound launch sizes the HBM round trip of a kernel's first loads overlaps the tail of
+// its predecessor instead of starting behind griddepcontrol.wait.
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {   // bytes % 16 == 0
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void pdl_launch_dependents() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }

@@ -171,6 +171,19 @@ __global__ void __launch_bounds__(kCtaThreads, 2) fwd_kernel(Args a) {
     float* my_slab0 = slab[0] + (grp * (gt >> 5)) * P;
     float* my_slab1 = slab[1] + (grp * (gt >> 5)) * P;
 
+    // hint this thread's first loads into L2 while the previous kernel drains (see prefetch_l2):
+    // one lane per 128-byte line
+    if ((tg & 7) == 0) {
+        const int64_t t0 = ((int64_t)blockIdx.x * groups_per_cta + grp) * TB;
+#pragma unroll
+        for (int b = 0; b < TB; ++b) {
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) {
+                const int j = tg + k * gt;
+                if (t0 + b < a.n_tok && j < nvec) prefetch_l2(a.h + (t0 + b) * nvec + j);
+            }
+        }
+    }
     // no early pdl_launch_dependents() here: the forward leaves a free CTA slot per SM, and a
     // successor that moves in early slows this kernel down more than it gains (measured 3.5 vs
     // 3.1 us per 256-token launch); the trigger is implicit at completion

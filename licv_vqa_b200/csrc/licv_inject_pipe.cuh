@@ -108,6 +108,22 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
     return v;
 }
 
+#ifdef LICV_TRACE
+// debug build only: per CTA {entry, after griddepcontrol.wait, first stage landed, first reduction
+// done, loop done, d_shift out} in ns (globaltimer), of the LAST launch in this translation unit
+static __device__ unsigned long long g_pipe_trace[512 * 8];
+#define LICV_PIPE_STAMP(i)                                                                     \
+    do {                                                                                       \
+        if (threadIdx.x == 0 && blockIdx.x < 512) {                                            \
+            unsigned long long t_;                                                             \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                            \
+            g_pipe_trace[blockIdx.x * 8 + (i)] = t_;                                           \
+        }                                                                                      \
+    } while (0)
+#else
+#define LICV_PIPE_STAMP(i) do { } while (0)
+#endif
+
 struct PipeArgs {
     Args a;
     int n_stages;
@@ -136,6 +152,19 @@ __global__ void __launch_bounds__(kPipeThreads, 3) bwd_pipe_kernel(PipeArgs pa) 
     const unsigned char* hb = reinterpret_cast<const unsigned char*>(a.h);
     const unsigned char* gb = reinterpret_cast<const unsigned char*>(a.g);
 
+    LICV_PIPE_STAMP(0);
+    if (tid == 32) {
+        // hint the first stages' rows into L2 while the previous kernel drains (see prefetch_l2)
+        for (int it = 0; it < S; ++it) {
+            const int64_t batch = (int64_t)blockIdx.x + it * G;
+            if (batch >= pa.n_batches) break;
+            const int64_t t0 = batch * TB;
+            const int64_t left = a.n_tok - t0;
+            const uint32_t ntok = (uint32_t)(left < TB ? left : TB);
+            prefetch_l2_bulk(hb + t0 * kHRow, ntok * kHRow);
+            prefetch_l2_bulk(gb + t0 * kGRow, ntok * kGRow);
+        }
+    }
     if (tid == 0) {
         for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
         mbar_init_fence();
@@ -143,6 +172,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) bwd_pipe_kernel(PipeArgs pa) 
     pdl_launch_dependents();
     __syncthreads();
     pdl_wait();   // everything above ran while the previous kernel drained; global memory from here
+    LICV_PIPE_STAMP(1);
 
     uint64_t policy = 0;
     // issue the copies of this CTA's `it`-th batch into stage it % S
@@ -179,6 +209,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) bwd_pipe_kernel(PipeArgs pa) 
         const unsigned char* sh = ring + (size_t)stage * kStage;
         const unsigned char* sg = sh + TB * kHRow;
         mbar_wait(&full[stage], parity);
+        if (it == 0) LICV_PIPE_STAMP(2);
 
         float acc[P];
 #pragma unroll
@@ -215,6 +246,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) bwd_pipe_kernel(PipeArgs pa) 
             const int lane = tid & 31, warp = tid >> 5;
             if ((lane & (32 / P - 1)) == 0) my[warp * P + warp_value_index<P>(lane)] = acc[0];
             __syncthreads();
+            if (it == 0) LICV_PIPE_STAMP(3);
             if (tid == 0 && it > 0) produce(it - 1 + S);
 #pragma unroll
             for (int i = 0; i < P; ++i) acc[i] = 0.f;
@@ -276,6 +308,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) bwd_pipe_kernel(PipeArgs pa) 
     // serialise per address (~27 clocks per contending warp): 256 CTAs on one [d] vector cost
     // 3.5 us, which is what the cluster pre-reduction below buys back at the price of two cluster
     // barriers; with <= 16 CTAs per replica the atomics are free and the CTA leaves at once.
+    LICV_PIPE_STAMP(4);
     if (a.rows != nullptr) {
         float* row = a.rows + (int64_t)((int)blockIdx.x & a.row_mask) * (VPT * kPipeThreads * EPV);
 #pragma unroll
@@ -285,6 +318,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) bwd_pipe_kernel(PipeArgs pa) 
             for (int e = 0; e < EPV; e += 4)
                 red_add_v4(row + (int64_t)j * EPV + e, ds[k][e], ds[k][e + 1], ds[k][e + 2], ds[k][e + 3]);
         }
+        LICV_PIPE_STAMP(5);
         return;
     }
     const uint32_t C = cluster_num_ctas();

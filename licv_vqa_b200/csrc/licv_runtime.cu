@@ -59,14 +59,16 @@ __global__ void icv_scale_kernel(const float* __restrict__ alpha, const float* _
 }
 
 // one CTA per layer: d_vec = alpha_eff * d_icv, d_alpha = (d_icv . vec) * dsigmoid
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 icv_scale_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ vec,
                      const float* __restrict__ d_icv, float* __restrict__ d_vec,
                      float* __restrict__ d_alpha, int d, int use_sigmoid) {
     pdl_launch_dependents();
-    pdl_wait();
-    __shared__ float slab[8];
     const int l = blockIdx.x;
+    // the parameters are last step's: hint this thread's share into L2 ahead of the wait
+    if ((threadIdx.x & 7) == 0 && (int)threadIdx.x < d / 4) prefetch_l2(vec + (int64_t)l * d + threadIdx.x * 4);
+    pdl_wait();
+    __shared__ float slab[32];
     float a = alpha[l];
     float da = 1.0f;
     if (use_sigmoid) {
@@ -256,8 +258,20 @@ sumsq_kernel(const float* __restrict__ g, int64_t n, float prescale, float* __re
     pdl_wait();
     __shared__ float slab[8];
     float s = 0.f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x) {
+    // 128-bit loads where the buffer allows: one round trip per thread for the 131 104 floats of
+    // the ICV parameters instead of four dependent ones (the launch is latency-bound)
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = (reinterpret_cast<uintptr_t>(g) & 15u) == 0 ? (n >> 2) : 0;
+    for (int64_t i = gtid; i < n4; i += gstride) {
+        const float4 x = reinterpret_cast<const float4*>(g)[i];
+        const float a0 = x.x * prescale, a1 = x.y * prescale, a2 = x.z * prescale, a3 = x.w * prescale;
+        s = fmaf(a0, a0, s);
+        s = fmaf(a1, a1, s);
+        s = fmaf(a2, a2, s);
+        s = fmaf(a3, a3, s);
+    }
+    for (int64_t i = n4 * 4 + gtid; i < n; i += gstride) {
         const float x = g[i] * prescale;
         s = fmaf(x, x, s);
     }
@@ -282,10 +296,20 @@ struct AdamArgs {
     const float* partials; // or: n_partials sums of squares to be added in index order
     int n_partials;
     const unsigned* skip;  // if set and non-zero: the gradient is not trustworthy, leave everything as it is
+    int vec4;              // 128-bit accesses allowed (alignment, n_vec % 4 == 0)
 };
 
 __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
     pdl_launch_dependents();
+    // parameters and moments are last step's: hint them into L2 while the norm is still being summed
+    if (a.vec4 && (threadIdx.x & 7) == 0) {
+        const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i4 * 4 < a.n_vec + a.n_alpha) {
+            prefetch_l2(a.p + i4 * 4);
+            prefetch_l2(a.m + i4 * 4);
+            prefetch_l2(a.v + i4 * 4);
+        }
+    }
     pdl_wait();
     // a failed gradient exchange (a peer never delivered) must not move the parameters
     if (a.skip != nullptr && *reinterpret_cast<const volatile unsigned*>(a.skip) != 0u) return;
@@ -310,15 +334,37 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
         coef *= fminf(c, 1.0f);
     }
     const int64_t n = a.n_vec + a.n_alpha;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const float lr = i < a.n_vec ? a.lr_vec : a.lr_alpha;
-        const float g = a.g[i] * coef;
-        float p = a.p[i] * (1.0f - lr * a.wd);
-        const float m = a.beta1 * a.m[i] + (1.0f - a.beta1) * g;
-        const float v = a.beta2 * a.v[i] + (1.0f - a.beta2) * g * g;
+    auto update = [&](float lr, float graw, float& p, float& m, float& v) {
+        const float g = graw * coef;
+        p = p * (1.0f - lr * a.wd);
+        m = a.beta1 * m + (1.0f - a.beta1) * g;
+        v = a.beta2 * v + (1.0f - a.beta2) * g * g;
         const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
         p -= (lr / a.bc1) * (m / denom);
+    };
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    // 128-bit accesses (a.vec4: 16-byte aligned buffers, n_vec a multiple of 4 so that no vector
+    // straddles the two learning rates): one round trip per thread instead of four dependent ones
+    const int64_t n4 = a.vec4 ? (n >> 2) : 0;
+    for (int64_t i4 = gtid; i4 < n4; i4 += gstride) {
+        const float lr = i4 * 4 < a.n_vec ? a.lr_vec : a.lr_alpha;
+        const float4 g4 = reinterpret_cast<const float4*>(a.g)[i4];
+        float4 p4 = reinterpret_cast<float4*>(a.p)[i4];
+        float4 m4 = reinterpret_cast<float4*>(a.m)[i4];
+        float4 v4 = reinterpret_cast<float4*>(a.v)[i4];
+        update(lr, g4.x, p4.x, m4.x, v4.x);
+        update(lr, g4.y, p4.y, m4.y, v4.y);
+        update(lr, g4.z, p4.z, m4.z, v4.z);
+        update(lr, g4.w, p4.w, m4.w, v4.w);
+        reinterpret_cast<float4*>(a.p)[i4] = p4;
+        reinterpret_cast<float4*>(a.m)[i4] = m4;
+        reinterpret_cast<float4*>(a.v)[i4] = v4;
+    }
+    for (int64_t i = n4 * 4 + gtid; i < n; i += gstride) {
+        const float lr = i < a.n_vec ? a.lr_vec : a.lr_alpha;
+        float p = a.p[i], m = a.m[i], v = a.v[i];
+        update(lr, a.g[i], p, m, v);
         a.p[i] = p; a.m[i] = m; a.v[i] = v;
     }
     __syncthreads();
@@ -385,7 +431,10 @@ extern "C" int licv_icv_scale_bwd(const float* alpha_raw, const float* vec, cons
     if (n_layers == 0) return LICV_OK;
     if (!alpha_raw || !vec || !d_icv || !d_vec) return LICV_ERR_NULL_POINTER;
     if (!aligned16(vec) || !aligned16(d_icv) || !aligned16(d_vec)) return LICV_ERR_MISALIGNED;
-    return launch_pdl(icv_scale_bwd_kernel, dim3(n_layers), dim3(256), 0,
+    // one 128-bit vector per thread where the row allows it (one round trip instead of four)
+    int threads = 256;
+    while (threads < 1024 && threads * 4 < d) threads *= 2;
+    return launch_pdl(icv_scale_bwd_kernel, dim3(n_layers), dim3(threads), 0,
                       reinterpret_cast<cudaStream_t>(stream), alpha_raw, vec, d_icv, d_vec, d_alpha_raw,
                       d, use_sigmoid);
 }
@@ -486,6 +535,9 @@ int launch_adamw_after_norm(float* param, const float* grad, float* exp_avg, flo
     a.norm_out = norm_out;
     a.acc = static_cast<float*>(workspace);
     a.ticket = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + 4);
+    a.vec4 = (n_vec % 4 == 0) &&
+             ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
+               reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15u) == 0;
     const int grid = (int)((n + 1023) / 1024 < 148 ? (n + 1023) / 1024 : 148);
     return launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, st, a);
 }

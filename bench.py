@@ -188,7 +188,9 @@ class HotPath:
         self.v = torch.zeros(L * d + L, **f32)
         self.icv = torch.empty(L, d, **f32)
         self.sink = torch.zeros(L, d, **f32)
-        self.losses = torch.zeros(4, **f32)
+        # N > 1: the loss kernel writes (kl, ce, total) straight into the tail of the flat gradient
+        # buffer, so the logged scalars ride along in the one exchange without a copy launch
+        self.losses = self.grad[L * d + L:] if world > 1 else torch.zeros(4, **f32)
         self.norm = torch.zeros(1, **f32)
         self.kl_tea_row = torch.empty(B * T, dtype=torch.int32, device=device)
         self.ce_label = torch.empty(B * T, dtype=torch.int64, device=device)
@@ -264,9 +266,6 @@ class HotPath:
         self._chk(lib.licv_icv_scale_bwd(alpha_p, vec_p, self.sink.data_ptr(), g,
                                          g + 4 * self.n_vec, L, d, int(CFG["use_sigmoid"]), st),
                   "icv_scale_bwd")
-        if self.world > 1:
-            # logged scalars ride in the tail of the same flat buffer (one exchange per step)
-            self.grad[self.n_vec + self.n_alpha:self.n_vec + self.n_alpha + 3].copy_(self.losses[:3])
 
     def optimize(self):
         """(N > 1: exchange of the flat gradient, fused with) clip + AdamW."""
@@ -865,6 +864,46 @@ def main():
         ms_per_step = sec / args.steps * 1e3
         value = CFG["batch_per_gpu"] * world / (sec / args.steps)
 
+        # ---- N > 1: what each GPU needs for the step's own work (no exchange, no optimizer) ------
+        # The ranks meet once per step, so the job runs at the pace of the slowest GPU: its compute
+        # time, next to the N = 1 line's, tells GPU-to-GPU spread apart from the cost of the exchange.
+        per_rank_compute_ms, exchange_only_ms = None, None
+        if world > 1:
+            hp.compute(batch)
+            stream.synchronize()
+            gc = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gc, stream=stream):
+                hp.compute(batch)
+            for _ in range(3):
+                gc.replay()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            for _ in range(20):
+                gc.replay()
+            c1.record(stream)
+            stream.synchronize()
+            mine = torch.tensor([c0.elapsed_time(c1) / 20], device=device)
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            torch.distributed.all_gather(allr, mine)
+            per_rank_compute_ms = [round(float(x), 4) for x in allr]
+            # the exchange + optimizer alone, back to back on every rank (same count everywhere)
+            go = torch.cuda.CUDAGraph()
+            hp.optimize()
+            stream.synchronize()
+            with torch.cuda.graph(go, stream=stream):
+                hp.optimize()
+            torch.distributed.barrier()
+            for _ in range(3):
+                go.replay()
+            c0.record(stream)
+            for _ in range(20):
+                go.replay()
+            c1.record(stream)
+            stream.synchronize()
+            exchange_only_ms = round(c0.elapsed_time(c1) / 20, 4)
+            hp.step(batch)                       # parameters of all ranks advance together again
+            stream.synchronize()
+
         # ---- dominant kernel, per launch, CUDA events on the launching stream -------------------
         L, d = CFG["layers"], CFG["d"]
         n_tok = CFG["batch_per_gpu"] * CFG["student_tokens"]
@@ -958,6 +997,13 @@ def main():
         "roofline": roofline, "clocks": clocks.summary(),
         "gpu_launches": (HotPath.LAUNCHES_PER_STEP) * args.steps,
     }
+    if per_rank_compute_ms:
+        line["per_rank_compute_ms"] = {
+            "values": per_rank_compute_ms, "slowest": max(per_rank_compute_ms), "fastest": min(per_rank_compute_ms),
+            "exchange_and_adamw_alone_ms": exchange_only_ms,
+            "how": "the step WITHOUT exchange and optimizer (icv_scale .. icv_scale_bwd) as a CUDA graph on "
+                   "every rank, 20 replays after the timed region: the ranks meet once per step, so "
+                   "ms_per_step tracks the slowest GPU's value plus exchange + AdamW"}
     if checks:
         line["checks"] = checks
 

@@ -316,15 +316,20 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
     // every CTA reads the norm before taking a ticket; the last ticket holder clears the workspace
     float coef = a.prescale;
     float sumsq;
-    if (a.partials != nullptr) {   // fixed-order sum: the same bits in every CTA and on every rank
-        __shared__ float s_sumsq;
-        if (threadIdx.x == 0) {
-            float t = 0.f;
-            for (int i = 0; i < a.n_partials; ++i) t += a.partials[i];
-            s_sumsq = t;
-        }
+    if (a.partials != nullptr) {
+        // fixed-order sum: the same bits in every CTA and on every rank.  A fixed TREE, not one
+        // thread walking the ~260 partials (each load waited for the one before: ~15 us of every
+        // multi-GPU step): thread t takes partials t, t + 256, ..., then the shuffle butterfly and
+        // the eight warp sums in index order - the same association everywhere
+        __shared__ float s_part[8];
+        float t = 0.f;
+        for (int i = threadIdx.x; i < a.n_partials; i += 256) t += a.partials[i];
+        t = warp_sum(t);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = t;
         __syncthreads();
-        sumsq = s_sumsq;
+        sumsq = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sumsq += s_part[w];
     } else {
         sumsq = *reinterpret_cast<volatile float*>(a.acc);
     }

@@ -668,6 +668,8 @@ def run_e2e_host(hp, steps, warmup, seed):
 
     seg = [0.0, 0.0, 0.0, 0.0]    # LICV_E2E_SEGMENTS=1: host prologue / call issue / drain / host optimizer
     want_seg = env_int("LICV_E2E_SEGMENTS", 0) != 0
+    phase = [0.0, 0.0, 0.0]       # LICV_E2E_PHASES=1: forward launches / loss / backward launches, synced apart
+    want_phases = env_int("LICV_E2E_PHASES", 0) != 0
 
     def step():
         t_a = time.perf_counter()
@@ -686,10 +688,16 @@ def run_e2e_host(hp, steps, warmup, seed):
                                                        icv_h[l].data_ptr(), out_h[l].data_ptr(),
                                                        n_tok, d, hp.code, hp.code, hp.flags),
                          "inject_fwd_host_save")
+        if want_phases:     # diagnostic only: a sync between the phases gives each phase's own link rate
+            hp.abi.check(lib.licv_host_sync(sess), "host_sync")
+            t_p1 = time.perf_counter()
         hp.abi.check(lib.licv_kd_loss_fwd_bwd_host(
             sess, hb["stu"].data_ptr(), dstu_h.data_ptr(), hb["tea"].data_ptr(), ktr.data_ptr(),
             lab.data_ptr(), n_kl, n_ce, CFG["temperature"], CFG["kl_eps"], CFG["hard_loss_weight"],
             0, 1.0, loss_h.data_ptr(), n_tok, B * T4, V, hp.code, 16), "kd_loss_host")
+        if want_phases:
+            hp.abi.check(lib.licv_host_sync(sess), "host_sync")
+            t_p2 = time.perf_counter()
         for l in reversed(range(L)):
             hp.abi.check(lib.licv_inject_bwd_host_saved(sess, l, hb["g"][l].data_ptr(),
                                                         icv_h[l].data_ptr(), dh_h[l].data_ptr(),
@@ -698,6 +706,9 @@ def run_e2e_host(hp, steps, warmup, seed):
         t_c = time.perf_counter()
         hp.abi.check(lib.licv_host_sync(sess), "host_sync")
         t_d = time.perf_counter()
+        if want_phases:
+            for i, v in enumerate((t_p1 - t_b, t_p2 - t_p1, t_d - t_p2)):
+                phase[i] += v
         # autograd of a2, then f2: global-norm clip + AdamW with the two learning rates
         d_vec = alpha.unsqueeze(-1) * ds_h
         d_alpha = (ds_h * vec).sum(1)
@@ -715,6 +726,7 @@ def run_e2e_host(hp, steps, warmup, seed):
     for _ in range(warmup):
         step()
     seg[:] = [0.0, 0.0, 0.0, 0.0]
+    phase[:] = [0.0, 0.0, 0.0]
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
@@ -722,6 +734,14 @@ def run_e2e_host(hp, steps, warmup, seed):
     if want_seg:
         print("e2e segments ms/step: prologue %.3f issue %.3f drain %.3f optimizer %.3f of %.3f" %
               tuple([1e3 * v / steps for v in seg] + [1e3 * dt]), file=sys.stderr, flush=True)
+    if want_phases:
+        fb = L * n_tok * d * es
+        lb = (n_tok + B * T4) * V * es
+        ms = [1e3 * v / steps for v in phase]
+        print("e2e phases (synced apart) ms/step: fwd %.3f (%.1f GB/s each way) loss %.3f (in %.1f GB/s) "
+              "bwd %.3f (%.1f GB/s each way) of %.3f" %
+              (ms[0], fb / ms[0] / 1e6, ms[1], lb / ms[1] / 1e6, ms[2], fb / ms[2] / 1e6, 1e3 * dt),
+              file=sys.stderr, flush=True)
     lib.licv_host_session_destroy(sess)
     # bytes that actually cross the link per step: h (once) and g per layer, the shift twice,
     # student + teacher logits, the two row lists; back: out and dh per layer, d_shift, d(logits)

@@ -466,6 +466,8 @@ __global__ void __launch_bounds__(NT, (NV <= 4 ? 768 / NT : 1)) kd_loss_cluster_
 // prefetched into registers right after sweep B.  16-bit logits, V <= 32760.
 // =================================================================================================
 
+constexpr int kMaxOrdered = 1024;   // launches of up to this many rows are worked in cost order
+
 template <int DT, int kMT, int kMNV>
 __global__ void __launch_bounds__(kMT, 1) kd_loss_tmem_kernel(KdArgs a) {
     constexpr int EPV = Fmt<DT>::kPerVec;   // 8
@@ -482,6 +484,10 @@ __global__ void __launch_bounds__(kMT, 1) kd_loss_tmem_kernel(KdArgs a) {
     __shared__ float s_tot[2 * kMW];
     __shared__ int s_last;
     __shared__ int s_tr[kMeta], s_lab[kMeta];               // (teacher row, label) of the next rows
+    // Work order (see build_order below): rows sorted by cost class, dealt to the CTAs in snake order
+    constexpr int kOrdRounds = (kMaxOrdered + kMT - 1) / kMT;
+    __shared__ uint16_t s_order[kMaxOrdered];
+    __shared__ int s_ocnt[3 * kOrdRounds * kMW];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (warp == 0) {
@@ -581,29 +587,94 @@ __global__ void __launch_bounds__(kMT, 1) kd_loss_tmem_kernel(KdArgs a) {
         return make_float2(warp_sum(sx), warp_sum(sy));
     };
 
-    int64_t r = blockIdx.x;
     const int64_t stride = gridDim.x;
+    // Work order.  A KL row costs about two CE-only rows (two cached streams, three sweeps) and a
+    // row in neither loss only a zero fill, and this kernel runs the launches with a few rows per
+    // SM (the training step: 256 rows on 148 SMs), where dealing rows r, r + G, ... to CTA r gave
+    // some SMs a KL row AND a second row while the launch waited for them.  Every CTA therefore
+    // sorts the rows by class (KL, CE only, neither; stable, from the row lists alone - integer
+    // work, the same in every CTA) and the sorted list is dealt in snake order (pass 0: CTA b takes
+    // item b, pass 1: item 2G-1-b, ...), the longest-first rule for identical machines: the SMs
+    // that got the dear rows get the cheap second rows, or none.  Results do not depend on which
+    // CTA works a row (per-row values, reduced in row order at the end).
+    const bool ordered = a.n_rows > stride && a.n_rows <= kMaxOrdered;
+    if (ordered) {
+        int cls[kOrdRounds], before[kOrdRounds];
+#pragma unroll
+        for (int q = 0; q < kOrdRounds; ++q) {
+            const int64_t t = (int64_t)q * kMT + tid;
+            int c = 3;
+            if (t < a.n_rows) c = fetch_tr(t) >= 0 ? 0 : (fetch_lab(t) != kLabNone ? 1 : 2);
+            cls[q] = c;
+            before[q] = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const unsigned b = __ballot_sync(0xffffffffu, c == k);
+                if (c == k) before[q] = __popc(b & ((1u << lane) - 1u));
+                if (lane == 0) s_ocnt[(k * kOrdRounds + q) * kMW + warp] = __popc(b);
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {   // exclusive scan of the 3 * rounds * warps counts, class-major
+            constexpr int kN = 3 * kOrdRounds * kMW, kPer = (kN + 31) / 32;
+            int v[kPer], sum = 0;
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) {
+                const int idx = lane * kPer + i;
+                v[i] = idx < kN ? s_ocnt[idx] : 0;
+                sum += v[i];
+            }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            int run = incl - sum;
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) {
+                const int idx = lane * kPer + i;
+                if (idx < kN) s_ocnt[idx] = run;
+                run += v[i];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kOrdRounds; ++q)
+            if (cls[q] < 3)
+                s_order[s_ocnt[(cls[q] * kOrdRounds + q) * kMW + warp] + before[q]] = (uint16_t)(q * kMT + tid);
+        // (the barrier inside fill_meta publishes s_order)
+    }
+    // the row this CTA works as its `ord`-th, or n_rows when it has no such row
+    auto row_of = [&](int ord) -> int64_t {
+        const int64_t b = blockIdx.x;
+        const int64_t pos = (int64_t)ord * stride + ((ordered && (ord & 1)) ? stride - 1 - b : b);
+        if (pos >= a.n_rows) return a.n_rows;
+        return ordered ? (int64_t)s_order[pos] : pos;
+    };
     // Row descriptors come from shared memory, refilled kMeta rows at a time: a label load issued
     // behind the next row's prefetch and narrowed at once stalled every warp for a full HBM round
     // trip per row (6 % of the kernel in one IADD3), and carrying the raw 64-bit label a row
     // instead costs two registers this kernel does not have.
-    auto fill_meta = [&](int64_t r0) {
+    auto fill_meta = [&](int ord0) {
         __syncthreads();
         if (tid < kMeta) {
-            const int64_t rr = r0 + (int64_t)tid * stride;
+            const int64_t rr = row_of(ord0 + tid);
             s_tr[tid] = fetch_tr(rr);
             s_lab[tid] = fetch_lab(rr);
         }
         __syncthreads();
     };
     int it = 0, meta0 = 0;                                  // this CTA's row ordinal, first cached ordinal
-    fill_meta(r);
+    fill_meta(0);
+    int64_t r = row_of(0);
     int tr = s_tr[0], lab = s_lab[0];
     if (r < a.n_rows) load_raw(r, tr, lab);
-    for (; r < a.n_rows; r += stride, ++it) {
-        const int64_t rn = r + stride;
+    int64_t rn;
+    for (; r < a.n_rows; r = rn, ++it) {
+        rn = row_of(it + 1);
         if (it + 1 - meta0 == kMeta) {
-            fill_meta(rn);
+            fill_meta(it + 1);
             meta0 = it + 1;
         }
         const bool has_kl = tr >= 0, has_ce = lab != kLabNone;

@@ -13,9 +13,9 @@ non-pad position a CE row, hard_loss_weight = 0.5), on synthetic tensors:
     32 x  out_l = inject(h_l, icv_l)                           licv_inject_fwd
     row pairing + labels, KL + 0.5 CE fwd+bwd on the logits     licv_kd_prepare_rows, licv_kd_loss_fwd_bwd
     32 x  dh_l, replicas_l += inject_bwd(h_l, g_l, icv_l)       licv_inject_bwd_spread
-    d_icv = sum of the replicas; d_v, d_alpha                   licv_reduce_rows, licv_icv_scale_bwd
-    (N > 1) all-reduce of the flat ICV gradient (131 104 fp32)  NCCL
-    clip + AdamW on the flat ICV parameters                     licv_adamw_step
+    d_icv = sum of the replicas; d_v, d_alpha; squared norms    licv_icv_grad_finish
+    (N > 1) exchange of the flat ICV gradient (131 104 fp32) fused with, (N = 1) just
+    clip + AdamW on the flat ICV parameters                     licv_dp_allreduce_adamw / licv_adamw_step_partials
 
 The frozen tower's GEMMs that produce h_l, g_l and the logits are stock cuBLAS and out of scope
 (BASELINE.json north_star); they are replaced here by resident synthetic tensors, a distinct
@@ -166,7 +166,14 @@ class ClockSampler:
 # the step, on resident tensors (C ABI launches on torch's current stream)
 # ------------------------------------------------------------------------------------------------
 class HotPath:
-    LAUNCHES_PER_STEP = 1 + 32 + 1 + 1 + 1 + 32 + 1 + 2   # + NCCL's own kernel when world > 1
+    @property
+    def launches_per_step(self):
+        """icv_scale, 32 x fwd, row prep, loss, 32 x bwd, the tail (1 fused / 2 split), the optimizer
+        (N = 1: AdamW alone after the fused tail, else sum of squares / exchange + AdamW); NCCL's own
+        kernel comes on top when that path is selected at N > 1."""
+        tail = 2 if self.split_tail else 1
+        opt = 1 if (self.world == 1 and not self.split_tail) else 2
+        return 1 + 32 + 1 + 1 + 32 + tail + opt
 
     def __init__(self, device, dtype, world):
         from licv_vqa_b200 import _abi, ops
@@ -192,6 +199,8 @@ class HotPath:
         # buffer, so the logged scalars ride along in the one exchange without a copy launch
         self.losses = self.grad[L * d + L:] if world > 1 else torch.zeros(4, **f32)
         self.norm = torch.zeros(1, **f32)
+        self.norm_partials = torch.zeros(L, **f32)
+        self.split_tail = env_int("LICV_BENCH_SPLIT_TAIL", 0) != 0
         self.kl_tea_row = torch.empty(B * T, dtype=torch.int32, device=device)
         self.ce_label = torch.empty(B * T, dtype=torch.int64, device=device)
         self.counts = torch.zeros(4, dtype=torch.int32, device=device)
@@ -199,7 +208,8 @@ class HotPath:
                               device=device)
         self.opt_ws = torch.zeros(16, dtype=torch.uint8, device=device)
         # the backward launches add their d_shift into replicas of the [L, d] gradient (zero between steps)
-        self.n_rows = self.lib.licv_inject_bwd_rows(B * T, d, self.code, self.code)
+        self.n_rows = (env_int("LICV_BENCH_ROWS", 0) or
+                       self.lib.licv_inject_bwd_rows(B * T, d, self.code, self.code))
         self.rows = torch.zeros(L, self.n_rows, d, **f32)
         self.out = [torch.empty(B * T, d, dtype=dtype, device=device) for _ in range(L)]
         self.dh = [torch.empty(B * T, d, dtype=dtype, device=device) for _ in range(L)]
@@ -259,13 +269,21 @@ class HotPath:
                 batch["h"][l].data_ptr(), batch["g"][l].data_ptr(), self.icv[l].data_ptr(),
                 self.dh[l].data_ptr(), self.rows[l].data_ptr(), R, n_tok, d, self.code, self.code,
                 self.flags, st), "inject_bwd_spread")
-        # d_icv = sum of the replicas (which the launch leaves zero for the next step)
-        self._chk(lib.licv_reduce_rows(self.rows.data_ptr(), self.sink.data_ptr(), L, R, R * d, d, 0, 1,
-                                       st), "reduce_rows")
+        # ONE launch: d_icv = sum of the replicas (left zero for the next step), d_vec, d_alpha and
+        # the per-layer squared norms the optimizer clips by (LICV_BENCH_SPLIT_TAIL=1: the separate
+        # licv_reduce_rows + licv_icv_scale_bwd launches, the optimizer sums the squares itself)
         g = self.grad.data_ptr()
-        self._chk(lib.licv_icv_scale_bwd(alpha_p, vec_p, self.sink.data_ptr(), g,
-                                         g + 4 * self.n_vec, L, d, int(CFG["use_sigmoid"]), st),
-                  "icv_scale_bwd")
+        if self.split_tail:
+            self._chk(lib.licv_reduce_rows(self.rows.data_ptr(), self.sink.data_ptr(), L, R, R * d, d,
+                                           0, 1, st), "reduce_rows")
+            self._chk(lib.licv_icv_scale_bwd(alpha_p, vec_p, self.sink.data_ptr(), g,
+                                             g + 4 * self.n_vec, L, d, int(CFG["use_sigmoid"]), st),
+                      "icv_scale_bwd")
+            return
+        self._chk(lib.licv_icv_grad_finish(self.rows.data_ptr(), R, R * d, alpha_p, vec_p,
+                                           self.sink.data_ptr(), g, g + 4 * self.n_vec,
+                                           self.norm_partials.data_ptr(), 1.0 / self.world, L, d,
+                                           int(CFG["use_sigmoid"]), 0, 1, st), "icv_grad_finish")
 
     def optimize(self):
         """(N > 1: exchange of the flat gradient, fused with) clip + AdamW."""
@@ -280,6 +298,14 @@ class HotPath:
             return
         if self.world > 1:
             torch.distributed.all_reduce(self.grad)
+        if self.world == 1 and not self.split_tail:
+            # the squared norm comes per layer from licv_icv_grad_finish: no sum-of-squares launch
+            self._chk(lib.licv_adamw_step_partials(
+                p, g, self.m.data_ptr(), self.v.data_ptr(), self.n_vec, self.n_alpha, 1e-4, 1e-2, 0.9,
+                0.999, 1e-8, 1e-3, self.step_no, 1.0, 1.0, self.norm.data_ptr(),
+                self.opt_ws.data_ptr(), self.norm_partials.data_ptr(), CFG["layers"], st),
+                "adamw_step_partials")
+            return
         self._chk(lib.licv_adamw_step(p, g, self.m.data_ptr(), self.v.data_ptr(), self.n_vec,
                                       self.n_alpha, 1e-4, 1e-2, 0.9, 0.999, 1e-8, 1e-3,
                                       self.step_no, 1.0 / self.world, 1.0, self.norm.data_ptr(),
@@ -497,7 +523,11 @@ def oracle_check(hp, batch):
                           CFG["kl_eps"], CFG["hard_loss_weight"], logit_fmt=CFG["dtype"])
     got = [float(x) for x in hp.losses[:3].cpu()]
     rows = [0, T - 2, T - 1, B * T - 3, B * T - 1]
-    return {"loss_rel_err": abs(got[2] - want["loss"]) / abs(want["loss"]),
+    extra = {}
+    if not hp.split_tail:   # the squared norm licv_icv_grad_finish hands to the optimizer
+        want_sq = (np.square(d_vec_o).sum() + np.square(d_alpha_o).sum()) / hp.world ** 2
+        extra["grad_sq_norm_rel_err"] = abs(float(host(hp.norm_partials).sum()) - want_sq) / want_sq
+    return {**extra, "loss_rel_err": abs(got[2] - want["loss"]) / abs(want["loss"]),
             "kl_rel_err": abs(got[0] - want["kl"]) / abs(want["kl"]),
             "ce_rel_err": abs(got[1] - want["ce"]) / abs(want["ce"]),
             "d_icv_rel_err_worst_layer": worst_ds, "dh_rel_err": worst_dh,
@@ -1015,13 +1045,13 @@ def main():
         "step_ms": {"median": step_stats[0], "p90": step_stats[1], "max": step_stats[2],
                     "how": "CUDA event after every step of the timed region; max over ranks"},
         "roofline": roofline, "clocks": clocks.summary(),
-        "gpu_launches": (HotPath.LAUNCHES_PER_STEP) * args.steps,
+        "gpu_launches": hp.launches_per_step * args.steps,
     }
     if per_rank_compute_ms:
         line["per_rank_compute_ms"] = {
             "values": per_rank_compute_ms, "slowest": max(per_rank_compute_ms), "fastest": min(per_rank_compute_ms),
             "exchange_and_adamw_alone_ms": exchange_only_ms,
-            "how": "the step WITHOUT exchange and optimizer (icv_scale .. icv_scale_bwd) as a CUDA graph on "
+            "how": "the step WITHOUT exchange and optimizer (icv_scale .. icv_grad_finish) as a CUDA graph on "
                    "every rank, 20 replays after the timed region: the ranks meet once per step, so "
                    "ms_per_step tracks the slowest GPU's value plus exchange + AdamW"}
     if checks:

@@ -119,6 +119,19 @@ int licv_inject_bwd_spread(const void* h, const void* g, const float* shift, voi
  * accumulation over micro-batches), 0 overwrites it; clear != 0 zero-fills the rows read. */
 int licv_reduce_rows(float* rows, float* out, int n_layers, int n_rows, int64_t layer_stride, int d,
                      int accumulate, int clear, licv_stream_t stream);
+/* The tail of a backward pass in ONE launch: licv_reduce_rows, licv_icv_scale_bwd (the autograd of
+ * icv = alpha.unsqueeze(-1) * in_context_vector, icv_src/icv_module.py:89-92) and the optimizer's
+ * sum of squares.  Per layer l: d_icv[l] = sum of the n_rows replicas (written if d_icv != NULL;
+ * the replicas are zero-filled if clear != 0), d_vec[l] (+)= alpha_eff[l] * d_icv[l],
+ * d_alpha_raw[l] (+)= (d_icv[l] . vec[l]) * dsigmoid (NULL: alpha not trained), and
+ * norm_partials[l] (NULL: not wanted) = the squared L2 norm of grad_prescale * (d_vec[l],
+ * d_alpha_raw[l]) as STORED (after accumulation), summed in a fixed order - what
+ * licv_adamw_step_partials takes.  accumulate != 0: += into d_vec / d_alpha_raw (gradient
+ * accumulation over micro-batches), 0: overwrite. */
+int licv_icv_grad_finish(float* rows, int n_rows, int64_t layer_stride, const float* alpha_raw,
+                         const float* vec, float* d_icv, float* d_vec, float* d_alpha_raw,
+                         float* norm_partials, float grad_prescale, int n_layers, int d,
+                         int use_sigmoid, int accumulate, int clear, licv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * a6  VQAICVModule.get_mask (icv_src/icv_module.py:136-148)
@@ -241,6 +254,16 @@ int licv_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_
                     float beta2, float eps, float weight_decay, int64_t step, float grad_prescale,
                     float max_grad_norm, float* norm_out, void* workspace /* >= 16 B, zeroed */,
                     licv_stream_t stream);
+
+/* The same update with the squared gradient norm handed over as n_partials partial sums of
+ * (grad * grad_prescale)^2 - what licv_icv_grad_finish leaves per layer - added in a fixed order:
+ * ONE launch instead of two (no sum-of-squares kernel). */
+int licv_adamw_step_partials(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                             int64_t n_vec, int64_t n_alpha, float lr_vec, float lr_alpha,
+                             float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                             float grad_prescale, float max_grad_norm, float* norm_out,
+                             void* workspace /* >= 16 B, zeroed */, const float* norm_partials,
+                             int n_partials, licv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * e  data-parallel gradient exchange fused with the optimizer step, over NVLink peer memory

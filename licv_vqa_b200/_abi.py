@@ -34,6 +34,8 @@ SIGNATURES = {
     "licv_inject_bwd_rows": (_i32, [_i64, _i32, _i32, _i32]),
     "licv_inject_bwd_spread": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _u32, _vp]),
     "licv_reduce_rows": (_i32, [_vp, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _vp]),
+    "licv_icv_grad_finish": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i32, _i32,
+                                    _i32, _i32, _i32, _vp]),
     "licv_get_mask": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "licv_kd_prepare_rows": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32,
                                     _vp, _vp, _vp, _vp]),
@@ -50,6 +52,8 @@ SIGNATURES = {
     "licv_scale_inplace": (_i32, [_vp, _i64, _vp, _i32, _vp]),
     "licv_adamw_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32,
                                _i64, _f32, _f32, _vp, _vp, _vp]),
+    "licv_adamw_step_partials": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32,
+                                        _f32, _i64, _f32, _f32, _vp, _vp, _vp, _i32, _vp]),
     "licv_dp_region_bytes": (_i64, [_i64]),
     "licv_dp_region_alloc": (_i32, [_i64, C.POINTER(_vp), _vp]),
     "licv_dp_comm_create": (_i32, [C.POINTER(_vp), _i32, _i32, _vp, _vp, _i64]),

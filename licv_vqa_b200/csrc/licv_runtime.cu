@@ -97,6 +97,92 @@ icv_scale_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ 
     }
 }
 
+// The tail of a backward pass in ONE launch (reduce_rows + icv_scale_bwd + the optimizer's sum of
+// squares): one CTA per layer, one thread per four columns.  d_icv = sum of the replicas the
+// spread backward launches left (zero-filled again if `clear`), d_vec (+)= alpha_eff * d_icv,
+// d_alpha (+)= (d_icv . vec) * dsigmoid, partial[l] = |prescale * (d_vec row, d_alpha)|^2 of the
+// STORED values, summed in a fixed order (shuffle butterfly, then the warps in index order).
+__global__ void __launch_bounds__(1024, 1)
+icv_grad_finish_kernel(float* __restrict__ rows, int n_rows, int64_t layer_stride,
+                       const float* __restrict__ alpha, const float* __restrict__ vec,
+                       float* __restrict__ d_icv, float* __restrict__ d_vec,
+                       float* __restrict__ d_alpha, float* __restrict__ partial, float prescale,
+                       int d, int use_sigmoid, int accumulate, int clear) {
+    pdl_launch_dependents();
+    const int l = blockIdx.x;
+    const int d4 = d / 4;
+    // the parameters are last step's: hint this thread's share into L2 ahead of the wait
+    if ((threadIdx.x & 7) == 0 && (int)threadIdx.x < d4) prefetch_l2(vec + (int64_t)l * d + threadIdx.x * 4);
+    pdl_wait();
+    __shared__ float slab[2][32];
+    float a = alpha[l];
+    float da = 1.0f;
+    if (use_sigmoid) {
+        a = sigmoidf(a);
+        da = a * (1.0f - a);
+    }
+    const float4* v4 = reinterpret_cast<const float4*>(vec + (int64_t)l * d);
+    float4* o4 = reinterpret_cast<float4*>(d_vec + (int64_t)l * d);
+    float dot = 0.f, ss = 0.f;
+    for (int i = threadIdx.x; i < d4; i += blockDim.x) {
+        float4* src = reinterpret_cast<float4*>(rows + l * layer_stride) + i;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        int p = 0;
+        for (; p + 8 <= n_rows; p += 8) {
+            float4 r[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) r[u] = __ldcg(src + (int64_t)(p + u) * d4);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                g.x += r[u].x; g.y += r[u].y; g.z += r[u].z; g.w += r[u].w;
+            }
+        }
+        for (; p < n_rows; ++p) {
+            const float4 r = __ldcg(src + (int64_t)p * d4);
+            g.x += r.x; g.y += r.y; g.z += r.z; g.w += r.w;
+        }
+        if (clear) {   // the replicas are ready for the next backward pass
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < n_rows; ++q) src[(int64_t)q * d4] = z;
+        }
+        if (d_icv) reinterpret_cast<float4*>(d_icv + (int64_t)l * d)[i] = g;
+        const float4 v = v4[i];
+        dot = fmaf(g.x, v.x, dot); dot = fmaf(g.y, v.y, dot);
+        dot = fmaf(g.z, v.z, dot); dot = fmaf(g.w, v.w, dot);
+        float4 o = make_float4(a * g.x, a * g.y, a * g.z, a * g.w);
+        if (accumulate) {
+            const float4 old = o4[i];
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        o4[i] = o;
+        const float s0 = o.x * prescale, s1 = o.y * prescale, s2 = o.z * prescale, s3 = o.w * prescale;
+        ss = fmaf(s0, s0, ss); ss = fmaf(s1, s1, ss); ss = fmaf(s2, s2, ss); ss = fmaf(s3, s3, ss);
+    }
+    if (d_alpha == nullptr && partial == nullptr) return;
+    dot = warp_sum(dot);
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) {
+        slab[0][threadIdx.x >> 5] = dot;
+        slab[1][threadIdx.x >> 5] = ss;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float sd = 0.f, sq = 0.f;
+        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) {
+            sd += slab[0][w];
+            sq += slab[1][w];
+        }
+        if (d_alpha) {
+            float x = sd * da;
+            if (accumulate) x += d_alpha[l];
+            d_alpha[l] = x;
+            x *= prescale;
+            sq = fmaf(x, x, sq);
+        }
+        if (partial) partial[l] = sq;
+    }
+}
+
 // out[l][c] (+)= sum_p rows[l][p][c]: one thread per (layer, 4 columns), the rows are L2-resident
 // (the backward launches of this step wrote them)
 __global__ void __launch_bounds__(256)
@@ -181,6 +267,24 @@ kd_prepare_rows_kernel(const int64_t* __restrict__ s_ids, const int64_t* __restr
     const int ns = batch * Tq, nt = batch * Tt;
     if (threadIdx.x == 0) s_m = 0;
 
+    // The launch is a chain of global round trips, not work: everything this thread needs for its
+    // FIRST student row, teacher row and label is requested here, together (one round trip instead
+    // of three behind each other's barriers); rows past the first blockDim.x of a list take the loops.
+    const int i_first = threadIdx.x;
+    int64_t f_sid = pad, f_slen = 0, f_tid = pad, f_tlen = 0, f_next = -100, f_att = 1;
+    if (i_first < ns) {
+        f_sid = s_ids[i_first];
+        f_slen = s_len[i_first / Tq];
+        if (ce_label != nullptr && (i_first % Tq) + 1 < Tq) {
+            f_next = s_ids[i_first + 1];
+            if (s_att != nullptr) f_att = s_att[i_first + 1];
+        }
+    }
+    if (i_first < nt) {
+        f_tid = t_ids[i_first];
+        f_tlen = t_len[i_first / Tt];
+    }
+
     // student rows in row-major order -> rank
     int base = 0;
     for (int i0 = 0; i0 < ns; i0 += blockDim.x) {
@@ -188,7 +292,8 @@ kd_prepare_rows_kernel(const int64_t* __restrict__ s_ids, const int64_t* __restr
         bool sel = false;
         if (i < ns) {
             const int b = i / Tq, t = i - b * Tq;
-            sel = ((int64_t)t >= s_len[b]) && (s_ids[i] != pad);
+            sel = i0 == 0 ? (((int64_t)t >= f_slen) && (f_sid != pad))
+                          : (((int64_t)t >= s_len[b]) && (s_ids[i] != pad));
             kl_tea_row[i] = -1;
         }
         int tot;
@@ -206,7 +311,8 @@ kd_prepare_rows_kernel(const int64_t* __restrict__ s_ids, const int64_t* __restr
         bool sel = false;
         if (i < nt) {
             const int b = i / Tt, t = i - b * Tt;
-            sel = ((int64_t)t >= t_len[b]) && (t_ids[i] != pad);
+            sel = i0 == 0 ? (((int64_t)t >= f_tlen) && (f_tid != pad))
+                          : (((int64_t)t >= t_len[b]) && (t_ids[i] != pad));
         }
         int tot;
         const int rk = cta_rank(sel, warp_tot, &tot);
@@ -230,9 +336,10 @@ kd_prepare_rows_kernel(const int64_t* __restrict__ s_ids, const int64_t* __restr
             const int b = i / Tq, t = i - b * Tq;
             int64_t lab = -100;
             if (t + 1 < Tq) {
-                lab = s_ids[i + 1];
+                const bool first = i == i_first;
+                lab = first ? f_next : s_ids[i + 1];
                 if (ce_variant != 2) {
-                    if (s_att != nullptr && s_att[i + 1] == 0) lab = -100;
+                    if (s_att != nullptr && (first ? f_att : s_att[i + 1]) == 0) lab = -100;
                     if (ce_variant == 1 && lab == image_tok) lab = -100;
                 }
             }
@@ -463,6 +570,27 @@ extern "C" int licv_reduce_rows(float* rows, float* out, int n_layers, int n_row
                       accumulate, clear);
 }
 
+extern "C" int licv_icv_grad_finish(float* rows, int n_rows, int64_t layer_stride,
+                                    const float* alpha_raw, const float* vec, float* d_icv,
+                                    float* d_vec, float* d_alpha_raw, float* norm_partials,
+                                    float grad_prescale, int n_layers, int d, int use_sigmoid,
+                                    int accumulate, int clear, licv_stream_t stream) {
+    if (device_info().status != LICV_OK) return device_info().status;
+    if (n_layers < 0 || n_rows < 0 || d <= 0 || d % 4 != 0 || layer_stride % 4 != 0 ||
+        layer_stride < (int64_t)n_rows * d)
+        return LICV_ERR_BAD_DIM;
+    if (n_layers == 0) return LICV_OK;
+    if (!alpha_raw || !vec || !d_vec || (n_rows > 0 && !rows)) return LICV_ERR_NULL_POINTER;
+    if (!aligned16(rows) || !aligned16(vec) || !aligned16(d_vec) || !aligned16(d_icv))
+        return LICV_ERR_MISALIGNED;
+    int threads = 256;
+    while (threads < 1024 && threads * 4 < d) threads *= 2;
+    return launch_pdl(icv_grad_finish_kernel, dim3(n_layers), dim3(threads), 0,
+                      reinterpret_cast<cudaStream_t>(stream), rows, n_rows, layer_stride, alpha_raw, vec,
+                      d_icv, d_vec, d_alpha_raw, norm_partials, grad_prescale, d, use_sigmoid,
+                      accumulate, clear);
+}
+
 extern "C" int licv_get_mask(const int64_t* input_ids, const int64_t* mask_length,
                              int64_t pad_token_id, int batch, int seq_len, uint8_t* mask,
                              licv_stream_t stream) {
@@ -566,4 +694,22 @@ extern "C" int licv_adamw_step(float* param, const float* grad, float* exp_avg, 
     return launch_adamw_after_norm(param, grad, exp_avg, exp_avg_sq, n_vec, n_alpha, lr_vec, lr_alpha,
                                    beta1, beta2, eps, weight_decay, step, grad_prescale,
                                    max_grad_norm, norm_out, workspace, nullptr, 0, nullptr, st);
+}
+
+extern "C" int licv_adamw_step_partials(float* param, const float* grad, float* exp_avg,
+                                        float* exp_avg_sq, int64_t n_vec, int64_t n_alpha,
+                                        float lr_vec, float lr_alpha, float beta1, float beta2,
+                                        float eps, float weight_decay, int64_t step,
+                                        float grad_prescale, float max_grad_norm, float* norm_out,
+                                        void* workspace, const float* norm_partials, int n_partials,
+                                        licv_stream_t stream) {
+    if (device_info().status != LICV_OK) return device_info().status;
+    if (n_vec < 0 || n_alpha < 0 || step < 1 || n_partials < 1) return LICV_ERR_BAD_ARGUMENT;
+    if (n_vec + n_alpha == 0) return LICV_OK;
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !workspace || !norm_partials)
+        return LICV_ERR_NULL_POINTER;
+    return launch_adamw_after_norm(param, grad, exp_avg, exp_avg_sq, n_vec, n_alpha, lr_vec, lr_alpha,
+                                   beta1, beta2, eps, weight_decay, step, grad_prescale,
+                                   max_grad_norm, norm_out, workspace, norm_partials, n_partials,
+                                   nullptr, reinterpret_cast<cudaStream_t>(stream));
 }

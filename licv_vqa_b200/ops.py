@@ -224,6 +224,24 @@ class GradStore:
         return out
 
 
+def icv_grad_finish(rows, alpha_raw, vec, d_vec, d_alpha=None, d_icv=None, norm_partials=None,
+                    grad_prescale=1.0, use_sigmoid=False, accumulate=False, clear=True):
+    """The tail of a backward pass in one launch: ``rows`` [L, R, d] (the replicas the spread
+    backward launches left) -> d_icv (optional), d_vec (+)= alpha_eff * d_icv, d_alpha (+)=
+    (d_icv . vec) * dsigmoid, per-layer squared norms of ``grad_prescale`` * the stored gradient
+    (for ``adamw_step(norm_partials=...)``).  The autograd of icv_module.py:89-92 with the
+    replica sum in front and the optimizer's norm behind."""
+    _need_cuda(rows, alpha_raw, vec, d_vec)
+    L, R, d = rows.shape
+    for t in (rows, vec, d_vec):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise TypeError("icv_grad_finish: contiguous fp32 buffers")
+    _abi.check(_abi.load().licv_icv_grad_finish(
+        rows.data_ptr(), R, R * d, alpha_raw.data_ptr(), vec.data_ptr(), _ptr(d_icv), d_vec.data_ptr(),
+        _ptr(d_alpha), _ptr(norm_partials), float(grad_prescale), L, d, int(use_sigmoid),
+        int(accumulate), int(clear), _stream()), "licv_icv_grad_finish")
+
+
 class _Anchor(torch.autograd.Function):
     """icv -> a 1-element token handed to the FIRST hooked layer's injection.  That layer runs its
     backward last, so the token's gradient arrives when every layer has deposited its d_shift:
@@ -474,11 +492,24 @@ def kd_loss(stu, tea, kl_tea_row=None, ce_label=None, counts=None, n_kl=None, n_
 # ---------------------------------------------------------------------------------------------
 def adamw_step(param, grad, exp_avg, exp_avg_sq, n_vec, n_alpha, lr_vec, lr_alpha, step,
                beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-3, grad_prescale=1.0,
-               max_grad_norm=1.0, norm_out=None, workspace=None):
+               max_grad_norm=1.0, norm_out=None, workspace=None, norm_partials=None):
+    """``norm_partials``: fp32 partial sums of (grad * grad_prescale)^2 (what ``icv_grad_finish``
+    leaves per layer) - the update then is one launch, without the sum-of-squares kernel."""
     _need_cuda(param, grad, exp_avg, exp_avg_sq)
     if workspace is None:
         workspace = _optimizer_workspace(param.device)
     ws_ptr = workspace.data_ptr()
+    if norm_partials is not None:
+        _need_cuda(norm_partials)
+        if norm_partials.dtype != torch.float32 or not norm_partials.is_contiguous():
+            raise TypeError("norm_partials: contiguous fp32")
+        _abi.check(_abi.load().licv_adamw_step_partials(
+            param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), int(n_vec),
+            int(n_alpha), float(lr_vec), float(lr_alpha), float(beta1), float(beta2), float(eps),
+            float(weight_decay), int(step), float(grad_prescale), float(max_grad_norm),
+            _ptr(norm_out), ws_ptr, norm_partials.data_ptr(), norm_partials.numel(), _stream()),
+            "licv_adamw_step_partials")
+        return
     _abi.check(_abi.load().licv_adamw_step(
         param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), int(n_vec),
         int(n_alpha), float(lr_vec), float(lr_alpha), float(beta1), float(beta2), float(eps),

@@ -146,6 +146,62 @@ def test_adamw_step_vs_oracle(ops, n_vec, n_alpha, clip):
         assert rel_err(host(dm), m) < 1e-5 and rel_err(host(dv), v) < 5e-5
 
 
+@pytest.mark.parametrize("L,R,d,use_sigmoid,accumulate,train_alpha", [
+    (32, 16, 4096, False, False, True),     # the training step's tail
+    (2, 1, 512, True, True, True),          # configs[0] shape, sigmoid, gradient accumulation
+    (5, 3, 1000, True, False, False),       # odd replica count, d not a multiple of the CTA, alpha frozen
+    (3, 9, 8192, False, True, True),        # two sweeps per thread
+])
+def test_icv_grad_finish_equals_the_separate_tail(ops, L, R, d, use_sigmoid, accumulate, train_alpha):
+    """licv_icv_grad_finish = licv_reduce_rows + licv_icv_scale_bwd + the optimizer's sum of squares,
+    against float64 (icv_module.py:89-92 differentiated by hand) and, through
+    licv_adamw_step_partials, against the two-launch licv_adamw_step on the same gradient."""
+    rng = np.random.default_rng(L * 1000 + R)
+    rows = rng.normal(size=(L, R, d))
+    alpha = rng.normal(size=L)
+    vec = rng.normal(size=(L, d)) * 0.01
+    old_dv, old_da = rng.normal(size=(L, d)), rng.normal(size=L)
+    prescale = 0.25
+    f32 = dict(dtype=torch.float32, device="cuda")
+    t_rows = torch.tensor(rows, **f32)
+    t_alpha, t_vec = torch.tensor(alpha, **f32), torch.tensor(vec, **f32)
+    grad = torch.tensor(np.concatenate([old_dv.ravel(), old_da]), **f32)
+    d_vec, d_alpha = grad[:L * d].view(L, d), grad[L * d:]
+    d_icv = torch.empty(L, d, **f32)
+    partials = torch.full((L,), -1.0, **f32)
+    rows32 = host(t_rows)                        # the fp32 replicas the kernel sees (it clears them)
+    ops.icv_grad_finish(t_rows, t_alpha, t_vec, d_vec, d_alpha if train_alpha else None, d_icv, partials,
+                        grad_prescale=prescale, use_sigmoid=use_sigmoid, accumulate=accumulate)
+    a_eff = 1 / (1 + np.exp(-alpha)) if use_sigmoid else alpha
+    da = a_eff * (1 - a_eff) if use_sigmoid else np.ones(L)
+    want_icv = rows32.sum(1)
+    want_dv = a_eff[:, None] * want_icv + (host(torch.tensor(old_dv, **f32)) if accumulate else 0.0)
+    want_da = (want_icv * host(t_vec)).sum(1) * da + (host(torch.tensor(old_da, **f32)) if accumulate else 0.0)
+    assert rel_err(host(d_icv), want_icv) < 1e-6
+    assert rel_err(host(d_vec), want_dv) < 1e-6
+    if train_alpha:
+        assert rel_err(host(d_alpha), want_da) < 2e-5
+    else:
+        assert np.array_equal(host(d_alpha), host(torch.tensor(old_da, **f32)))     # untouched
+    want_sq = prescale ** 2 * (np.square(want_dv).sum(1) + (np.square(want_da) if train_alpha else 0.0))
+    assert rel_err(host(partials), want_sq) < 1e-5
+    assert float(t_rows.abs().max()) == 0.0      # the replicas are ready for the next pass
+    # the optimizer on those partials = the optimizer that sums the squares itself
+    n_vec, n_alpha = L * d, (L if train_alpha else 0)
+    g_used = grad[:n_vec + n_alpha].clone()
+    state = [torch.tensor(rng.normal(size=n_vec + n_alpha), **f32), torch.zeros(n_vec + n_alpha, **f32),
+             torch.zeros(n_vec + n_alpha, **f32)]
+    state2 = [t.clone() for t in state]
+    n1, n2 = torch.zeros(1, **f32), torch.zeros(1, **f32)
+    ops.adamw_step(state[0], g_used, state[1], state[2], n_vec, n_alpha, 1e-3, 1e-1, 1,
+                   grad_prescale=prescale, max_grad_norm=0.5, norm_out=n1)
+    ops.adamw_step(state2[0], g_used, state2[1], state2[2], n_vec, n_alpha, 1e-3, 1e-1, 1,
+                   grad_prescale=prescale, max_grad_norm=0.5, norm_out=n2, norm_partials=partials)
+    assert rel_err(host(n2), host(n1)) < 1e-6
+    for a, b in zip(state, state2):
+        assert rel_err(host(b), host(a)) < 1e-6
+
+
 def test_dp_optimizer_world1_matches_torch_adamw(ops):
     """ICVDataParallelOptimizer (flat views + fused kernel) against torch.optim.AdamW with the
     reference's two parameter groups, clip 1.0 and cosine warm-up (icv_module.py:171-209)."""

@@ -1039,7 +1039,8 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": CFG["dtype"] + " (fp32 accumulate)",
         "data": "synthetic", "config": config_of(world),
         "arm": {"grad_exchange": ("none (1 GPU)" if world == 1 else
-                                  "fused p2p exchange + AdamW over NVLink peer memory"
+                                  "fused p2p exchange (%s form) + AdamW over NVLink peer memory"
+                                  % ({"all": "all-to-all", "owner": "owner"}.get(os.environ.get("LICV_DP_ALGO", ""), "owner"))
                                   if hp.peer is not None else "nccl all_reduce" + hp.peer_note),
                 "cuda_graph": graph is not None, "gpu": torch.cuda.get_device_name(local)},
         "step_ms": {"median": step_stats[0], "p90": step_stats[1], "max": step_stats[2],

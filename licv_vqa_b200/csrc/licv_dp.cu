@@ -27,7 +27,14 @@
 // parity: a peer can only push step k + 2 after it has finished step k + 1, which needed this
 // rank's step-k+1 packets, which are pushed after this rank finished reading step k.  The step
 // counter lives in device memory, so the launch can be replayed from a CUDA graph.
+//
+// Two forms of the kernel share packets, slots, tags and error handling.  The all-to-all form is
+// the one described above.  The OWNER form (dp_exchange_owner_kernel, the default: see dp_algo)
+// gives every packet an owning rank - contributions go to the owner only, the owner pushes the
+// rank-order sum to everybody - which moves 2 (world - 1) / world of the buffer per GPU instead
+// of (world - 1) x it, for one more one-way trip; it measured faster at 2 and at 8 ranks.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -84,6 +91,7 @@ struct DpArgs {
     int rank, world;
     float prescale;       // 1 / world for the norm
     float* partial;       // [gridDim.x] per-CTA sums of squares (summed in fixed order later)
+    int64_t slice;        // owner form: packets per owning rank (owner of packet i = i / slice)
 };
 
 // one packet = two 8-byte elements {float bits | tag << 32}: each element is one scalar access
@@ -212,6 +220,130 @@ __global__ void __launch_bounds__(kDpThreads) dp_exchange_kernel(DpArgs a) {
     }
 }
 
+// The OWNER form of the same exchange, for many ranks.  The all-to-all form above moves
+// (world - 1) x the whole packet buffer out of and into every GPU (7.3 MB each way at world = 8:
+// bandwidth, ~13 us of every step); here packet i has an owning rank (i / slice): every rank pushes
+// its packet to the OWNER only, the owner adds the world's packets in rank order and pushes the sum
+// to every peer - 2 (world - 1) / world of the buffer per GPU and direction (1.8 MB at world = 8)
+// for one more one-way trip.  The sums land in the owner's source slot at the owner's slice, the
+// contributions in the sender's source slot at the receiver's slice: positions never collide, and
+// the same two parity slots serve (a rank two steps ahead implies every owner finished the step in
+// between, which implies every rank finished this one).  Same packets, tags, bounded waits, error
+// word and rank-order sums: every replica ends with the same bits as with the all-to-all form.
+__global__ void __launch_bounds__(kDpThreads) dp_exchange_owner_kernel(DpArgs a) {
+    __shared__ float slab[kDpThreads / 32];
+    licv::pdl_launch_dependents();
+    licv::pdl_wait();
+    char* local = a.region[a.rank];
+    unsigned long long* step_ctr = reinterpret_cast<unsigned long long*>(local + a.ctl_off);
+    unsigned* ticket = reinterpret_cast<unsigned*>(local + a.ctl_off + 8);
+    unsigned* error = ticket + 2;
+    const unsigned long long step = *step_ctr + 1;
+    const unsigned tag = (unsigned)step;
+    const int64_t parity_off = (int64_t)(step & 1ull) * kDpMaxWorld * a.slot_bytes;
+    const int64_t my_slot = parity_off + (int64_t)a.rank * a.slot_bytes;
+    const int tid = threadIdx.x;
+
+    // bounded wait for one packet of this step (false: the sender never delivered)
+    auto await = [&](const char* p, unsigned long long& lo, unsigned long long& hi) -> bool {
+        ld_packet(p, lo, hi);
+        if (packet_ok(lo, hi, tag)) return true;
+        const long long t0 = clock64();
+        do {
+            ld_packet(p, lo, hi);
+            if (clock64() - t0 > (1ll << 33)) {   // ~4 s
+                *error = 1u;
+                return false;
+            }
+        } while (!packet_ok(lo, hi, tag));
+        return true;
+    };
+
+    float sq = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * kDpThreads + tid; i < a.n_packets;
+         i += (int64_t)gridDim.x * kDpThreads) {
+        float f[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) f[k] = i * 2 + k < a.n ? a.grad[i * 2 + k] : 0.f;
+        const int own = (int)(i / a.slice);
+        float s[2] = {0.f, 0.f};
+        if (own != a.rank) {
+            // contribute to the owner, then take the owner's sum from LOCAL memory
+            char* owner_region = a.region[0];
+#pragma unroll
+            for (int p = 1; p < kDpMaxWorld; ++p)
+                if (p == own) owner_region = a.region[p];
+            st_packet(owner_region + my_slot + i * 16, half_packet(f[0], tag), half_packet(f[1], tag));
+            unsigned long long lo, hi;
+            if (!await(local + parity_off + (int64_t)own * a.slot_bytes + i * 16, lo, hi)) continue;
+            s[0] = __uint_as_float((unsigned)lo);
+            s[1] = __uint_as_float((unsigned)hi);
+        } else {
+            unsigned long long vlo[kDpMaxWorld], vhi[kDpMaxWorld];
+#pragma unroll
+            for (int p = 0; p < kDpMaxWorld; ++p)
+                if (p < a.world && p != a.rank)
+                    ld_packet(local + parity_off + (int64_t)p * a.slot_bytes + i * 16, vlo[p], vhi[p]);
+            bool dead = false;
+#pragma unroll
+            for (int p = 0; p < kDpMaxWorld; ++p)
+                if (p < a.world && p != a.rank && !packet_ok(vlo[p], vhi[p], tag) && !dead)
+                    dead = !await(local + parity_off + (int64_t)p * a.slot_bytes + i * 16, vlo[p], vhi[p]);
+            if (dead) continue;    // nobody gets this sum: every rank raises its error word
+#pragma unroll
+            for (int p = 0; p < kDpMaxWorld; ++p) {
+                if (p < a.world) {
+                    if (p == a.rank) {
+                        s[0] += f[0]; s[1] += f[1];
+                    } else {
+                        s[0] += __uint_as_float((unsigned)vlo[p]);
+                        s[1] += __uint_as_float((unsigned)vhi[p]);
+                    }
+                }
+            }
+            const unsigned long long plo = half_packet(s[0], tag), phi = half_packet(s[1], tag);
+#pragma unroll
+            for (int p = 0; p < kDpMaxWorld; ++p)
+                if (p < a.world && p != a.rank) st_packet(a.region[p] + my_slot + i * 16, plo, phi);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (i * 2 + k < a.n) a.grad[i * 2 + k] = s[k];
+            if (i * 2 + k < a.n_norm) {
+                const float x = s[k] * a.prescale;
+                sq = fmaf(x, x, sq);
+            }
+        }
+    }
+    sq = licv::warp_sum(sq);
+    if ((tid & 31) == 0) slab[tid >> 5] = sq;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int w = 0; w < kDpThreads / 32; ++w) t += slab[w];
+        a.partial[blockIdx.x] = t;
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+            *ticket = 0u;
+            *step_ctr = step;
+        }
+    }
+}
+
+// which form: LICV_DP_ALGO = all | owner | auto (auto: the owner form from kDpOwnerFromWorld ranks).
+// Measured under the driver's command (20 steps): N = 2 0.2914 (owner) vs 0.2929 ms (all), N = 8
+// 0.2968 vs 0.3062 ms - the posted 16-byte writes, not the extra trip, are what the exchange costs.
+constexpr int kDpOwnerFromWorld = 2;
+int dp_algo() {
+    static const int algo = [] {
+        const char* v = std::getenv("LICV_DP_ALGO");
+        if (v && std::strcmp(v, "all") == 0) return 1;
+        if (v && std::strcmp(v, "owner") == 0) return 2;
+        return 0;
+    }();
+    return algo;
+}
+
 }  // namespace
 
 #ifdef LICV_TRACE
@@ -338,8 +470,15 @@ extern "C" int licv_dp_allreduce_adamw(licv_dp_comm* c, float* param, float* gra
     a.world = c->world;
     a.prescale = 1.0f / (float)c->world;
     a.partial = reinterpret_cast<float*>(c->region[c->rank] + L.partial_off);
+    a.slice = (L.n_packets + c->world - 1) / c->world;
     const int grid = grid_of(L);
-    if (int rc = licv::launch_pdl(dp_exchange_kernel, dim3(grid), dim3(kDpThreads), 0, st, a)) return rc;
+    const int algo = dp_algo();
+    const bool owner_form = c->world > 1 && L.n_packets >= c->world &&
+                            (algo == 2 || (algo == 0 && c->world >= kDpOwnerFromWorld));
+    if (int rc = owner_form
+                     ? licv::launch_pdl(dp_exchange_owner_kernel, dim3(grid), dim3(kDpThreads), 0, st, a)
+                     : licv::launch_pdl(dp_exchange_kernel, dim3(grid), dim3(kDpThreads), 0, st, a))
+        return rc;
     return licv::launch_adamw_after_norm(param, grad, exp_avg, exp_avg_sq, n_vec, n_alpha, lr_vec,
                                          lr_alpha, beta1, beta2, eps, weight_decay, step,
                                          1.0f / (float)c->world, max_grad_norm, norm_out, workspace,

@@ -3,6 +3,9 @@
 // fused clip + AdamW step on the flat ICV parameter buffer (f2).
 #include <mutex>
 
+#include <cooperative_groups.h>
+#include <cstdlib>
+
 #include "licv_common.cuh"
 
 namespace licv {
@@ -171,6 +174,107 @@ icv_grad_finish_kernel(float* __restrict__ rows, int n_rows, int64_t layer_strid
         for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) {
             sd += slab[0][w];
             sq += slab[1][w];
+        }
+        if (d_alpha) {
+            float x = sd * da;
+            if (accumulate) x += d_alpha[l];
+            d_alpha[l] = x;
+            x *= prescale;
+            sq = fmaf(x, x, sq);
+        }
+        if (partial) partial[l] = sq;
+    }
+}
+
+// The same launch for wide layers: a thread-block cluster of kFinishCluster CTAs per layer, CTA c
+// takes the c-th share of the columns (one SM per layer could not pull its 16 replicas x 16 KB
+// out of L2 and zero them fast enough: 10 us for 32 layers), and the CTAs' (dot, sum of squares)
+// meet in CTA 0's shared memory (DSMEM stores, one cluster barrier), added in CTA order.
+constexpr int kFinishCluster = 4;
+__global__ void __launch_bounds__(256)
+icv_grad_finish_cluster_kernel(float* __restrict__ rows, int n_rows, int64_t layer_stride,
+                               const float* __restrict__ alpha, const float* __restrict__ vec,
+                               float* __restrict__ d_icv, float* __restrict__ d_vec,
+                               float* __restrict__ d_alpha, float* __restrict__ partial,
+                               float prescale, int d, int use_sigmoid, int accumulate, int clear) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    pdl_launch_dependents();
+    const int l = blockIdx.x / kFinishCluster, c = blockIdx.x % kFinishCluster;
+    const int d4 = d / 4;
+    const int per = (d4 + kFinishCluster - 1) / kFinishCluster;
+    const int lo = c * per, hi = lo + per < d4 ? lo + per : d4;
+    if ((threadIdx.x & 7) == 0 && lo + (int)threadIdx.x < hi)
+        prefetch_l2(vec + (int64_t)l * d + (lo + threadIdx.x) * 4);
+    pdl_wait();
+    __shared__ float slab[2][8];
+    __shared__ float met[2][kFinishCluster];   // CTA 0's: every CTA's (dot, sum of squares)
+    float a = alpha[l];
+    float da = 1.0f;
+    if (use_sigmoid) {
+        a = sigmoidf(a);
+        da = a * (1.0f - a);
+    }
+    const float4* v4 = reinterpret_cast<const float4*>(vec + (int64_t)l * d);
+    float4* o4 = reinterpret_cast<float4*>(d_vec + (int64_t)l * d);
+    float dot = 0.f, ss = 0.f;
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        float4* src = reinterpret_cast<float4*>(rows + l * layer_stride) + i;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        int p = 0;
+        for (; p + 8 <= n_rows; p += 8) {
+            float4 r[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) r[u] = __ldcg(src + (int64_t)(p + u) * d4);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                g.x += r[u].x; g.y += r[u].y; g.z += r[u].z; g.w += r[u].w;
+            }
+        }
+        for (; p < n_rows; ++p) {
+            const float4 r = __ldcg(src + (int64_t)p * d4);
+            g.x += r.x; g.y += r.y; g.z += r.z; g.w += r.w;
+        }
+        if (clear) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < n_rows; ++q) src[(int64_t)q * d4] = z;
+        }
+        if (d_icv) reinterpret_cast<float4*>(d_icv + (int64_t)l * d)[i] = g;
+        const float4 v = v4[i];
+        dot = fmaf(g.x, v.x, dot); dot = fmaf(g.y, v.y, dot);
+        dot = fmaf(g.z, v.z, dot); dot = fmaf(g.w, v.w, dot);
+        float4 o = make_float4(a * g.x, a * g.y, a * g.z, a * g.w);
+        if (accumulate) {
+            const float4 old = o4[i];
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        o4[i] = o;
+        const float s0 = o.x * prescale, s1 = o.y * prescale, s2 = o.z * prescale, s3 = o.w * prescale;
+        ss = fmaf(s0, s0, ss); ss = fmaf(s1, s1, ss); ss = fmaf(s2, s2, ss); ss = fmaf(s3, s3, ss);
+    }
+    dot = warp_sum(dot);
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) {
+        slab[0][threadIdx.x >> 5] = dot;
+        slab[1][threadIdx.x >> 5] = ss;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float sd = 0.f, sq = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            sd += slab[0][w];
+            sq += slab[1][w];
+        }
+        float* dst = cluster.map_shared_rank(&met[0][0], 0);
+        dst[c] = sd;
+        dst[kFinishCluster + c] = sq;
+    }
+    cluster.sync();
+    if (c == 0 && threadIdx.x == 0) {
+        float sd = 0.f, sq = 0.f;
+        for (int k = 0; k < kFinishCluster; ++k) {
+            sd += met[0][k];
+            sq += met[1][k];
         }
         if (d_alpha) {
             float x = sd * da;
@@ -583,6 +687,22 @@ extern "C" int licv_icv_grad_finish(float* rows, int n_rows, int64_t layer_strid
     if (!alpha_raw || !vec || !d_vec || (n_rows > 0 && !rows)) return LICV_ERR_NULL_POINTER;
     if (!aligned16(rows) || !aligned16(vec) || !aligned16(d_vec) || !aligned16(d_icv))
         return LICV_ERR_MISALIGNED;
+    static const bool cluster_form = [] {
+        const char* v = std::getenv("LICV_FINISH_CLUSTER");   // 0: one CTA per layer at any width (A/B)
+        return !(v && v[0] == '0');
+    }();
+    if (d >= 2048 && cluster_form) {   // wide layers: a cluster of CTAs per layer
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)n_layers * kFinishCluster);
+        cfg.blockDim = dim3(256);
+        cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+        cudaLaunchAttribute attr[2];
+        cfg.attrs = attr;
+        cfg.numAttrs = launch_attrs(attr, kFinishCluster);
+        return (int)cudaLaunchKernelEx(&cfg, icv_grad_finish_cluster_kernel, rows, n_rows, layer_stride,
+                                       alpha_raw, vec, d_icv, d_vec, d_alpha_raw, norm_partials,
+                                       grad_prescale, d, use_sigmoid, accumulate, clear);
+    }
     int threads = 256;
     while (threads < 1024 && threads * 4 < d) threads *= 2;
     return launch_pdl(icv_grad_finish_kernel, dim3(n_layers), dim3(threads), 0,

@@ -92,6 +92,54 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+# -------------------------------------------------------------------------------------------------
+# liblicv_torch.so: the TORCH_LIBRARY registration (csrc/licv_torch_ops.cpp), a host-only shim that
+# links liblicv_b200.so and libtorch.  g++ only (no kernel in it); one translation unit.
+# -------------------------------------------------------------------------------------------------
+TORCH_SRC = os.path.join(CSRC, "licv_torch_ops.cpp")
+TORCH_LIB = os.path.join(LIB_DIR, "liblicv_torch.so")
+TORCH_STAMP = os.path.join(LIB_DIR, "liblicv_torch.stamp")
+
+
+def _torch_digest():
+    import torch
+    h = hashlib.sha256()
+    h.update(torch.__version__.encode())
+    for f in (TORCH_SRC, os.path.join(INCLUDE, "licv_b200.h"), os.path.abspath(__file__)):
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def build_torch_ops(force: bool = False) -> str:
+    """Compile csrc/licv_torch_ops.cpp into lib/liblicv_torch.so against the installed torch."""
+    build()    # the C-ABI library it links
+    digest = _torch_digest()
+    if not force and os.path.exists(TORCH_LIB) and os.path.exists(TORCH_STAMP):
+        with open(TORCH_STAMP) as f:
+            if f.read().strip() == digest:
+                return TORCH_LIB
+    import torch
+    from torch.utils import cpp_extension as ce
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cuda_home = os.environ.get("CUDA_HOME") or "/usr/local/cuda"
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+           *[f"-I{p}" for p in ce.include_paths()], f"-I{cuda_home}/include", f"-I{INCLUDE}",
+           TORCH_SRC, "-o", TORCH_LIB,
+           f"-L{LIB_DIR}", "-llicv_b200", f"-L{tlib}", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch",
+           "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}"]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if p.returncode != 0:
+        sys.stderr.write(p.stdout)
+        raise RuntimeError(f"g++ failed on {TORCH_SRC}: {' '.join(cmd)}")
+    with open(TORCH_STAMP, "w") as f:
+        f.write(digest)
+    return TORCH_LIB
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(path)
+    print(build_torch_ops(force="--force" in sys.argv))

@@ -327,3 +327,33 @@ def test_torch_library_ops_are_registered_with_fake_kernels():
         stu = torch.empty(64, 32002, dtype=torch.float16, device="cuda")
         tot, kl, ce, d = torch.ops.licv.kd_loss(stu, stu, None, None, None, 64, 0, 1.0, 1e-6, 0.0, False, 16)
         assert tot.shape == () and d.shape == stu.shape and d.dtype == stu.dtype
+
+
+def test_registered_ops_have_no_cpu_kernel_and_a_cpp_autograd_formula():
+    """The operators come from C++ (csrc/licv_torch_ops.cpp: CUDA + Meta + Autograd keys).  A CPU
+    tensor fails in the dispatcher - there is no CPU path to fall back to - and the C++ autograd
+    formula is what a fake-tensor trace records (C++ nodes; shapes and dtypes of dh / d_shift / d stu)."""
+    import pytest
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from licv_vqa_b200 import torch_ops  # noqa: F401
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.licv.inject(torch.zeros(2, 64), torch.zeros(64), torch.float32, 0)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.licv.get_mask(torch.zeros(2, 8, dtype=torch.long), torch.zeros(2, dtype=torch.long), 0)
+    with FakeTensorMode():
+        h = torch.empty(4, 16, 4096, dtype=torch.bfloat16, device="cuda", requires_grad=True)
+        shift = torch.empty(4096, device="cuda", requires_grad=True)
+        out = torch.ops.licv.inject(h, shift, torch.bfloat16, 0)
+        assert out.requires_grad and "InjectFn" in out.grad_fn.name()      # the C++ node, not a Python one
+        # (running the backward needs the engine's CUDA device thread: tests/test_gpu_torch_ops.py)
+        dh, ds = torch.ops.licv.inject_bwd(h.detach(), out.detach(), shift.detach(), 0)
+        assert dh.shape == h.shape and dh.dtype == torch.bfloat16
+        assert ds.shape == shift.shape and ds.dtype == torch.float32
+        stu = torch.empty(6, 32002, dtype=torch.float16, device="cuda", requires_grad=True)
+        lab = torch.empty(6, dtype=torch.long, device="cuda")
+        total, kl, ce, dstu = torch.ops.licv.kd_loss(stu, stu.detach(), None, lab, None, 6, 6, 1.0, 1e-6, 0.5,
+                                                     False, 16)
+        assert total.requires_grad and not kl.requires_grad and not dstu.requires_grad
+        assert "KdLossFn" in total.grad_fn.name()
+        assert dstu.shape == stu.shape and dstu.dtype == torch.float16

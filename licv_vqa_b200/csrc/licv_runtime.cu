@@ -221,15 +221,19 @@ icv_grad_finish_cluster_kernel(float* __restrict__ rows, int n_rows, int64_t lay
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         float4* src = reinterpret_cast<float4*>(rows + l * layer_stride) + i;
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        // the first 16 replicas (all of them for the shapes licv_inject_bwd_rows answers) in ONE
+        // batch of loads: the launch is a chain of L2 round trips, not bandwidth
         int p = 0;
-        for (; p + 8 <= n_rows; p += 8) {
-            float4 r[8];
+        {
+            float4 r[16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) r[u] = __ldcg(src + (int64_t)(p + u) * d4);
+            for (int u = 0; u < 16; ++u)
+                r[u] = u < n_rows ? __ldcg(src + (int64_t)u * d4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < 16; ++u) {
                 g.x += r[u].x; g.y += r[u].y; g.z += r[u].z; g.w += r[u].w;
             }
+            p = n_rows < 16 ? n_rows : 16;
         }
         for (; p < n_rows; ++p) {
             const float4 r = __ldcg(src + (int64_t)p * d4);

@@ -528,6 +528,19 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
     pdl_wait();
     // a failed gradient exchange (a peer never delivered) must not move the parameters
     if (a.skip != nullptr && *reinterpret_cast<const volatile unsigned*>(a.skip) != 0u) return;
+    // this thread's first vector of gradient / parameter / moments is requested BEFORE the norm is
+    // summed: the launch is a chain of L2 round trips, and these four do not depend on the norm
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = a.vec4 ? ((a.n_vec + a.n_alpha) >> 2) : 0;
+    const bool first = gtid < n4;
+    float4 g4f = make_float4(0.f, 0.f, 0.f, 0.f), p4f = g4f, m4f = g4f, v4f = g4f;
+    if (first) {
+        g4f = reinterpret_cast<const float4*>(a.g)[gtid];
+        p4f = reinterpret_cast<float4*>(a.p)[gtid];
+        m4f = reinterpret_cast<float4*>(a.m)[gtid];
+        v4f = reinterpret_cast<float4*>(a.v)[gtid];
+    }
     // every CTA reads the norm before taking a ticket; the last ticket holder clears the workspace
     float coef = a.prescale;
     float sumsq;
@@ -562,12 +575,19 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
         const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
         p -= (lr / a.bc1) * (m / denom);
     };
-    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
     // 128-bit accesses (a.vec4: 16-byte aligned buffers, n_vec a multiple of 4 so that no vector
     // straddles the two learning rates): one round trip per thread instead of four dependent ones
-    const int64_t n4 = a.vec4 ? (n >> 2) : 0;
-    for (int64_t i4 = gtid; i4 < n4; i4 += gstride) {
+    if (first) {
+        const float lr = gtid * 4 < a.n_vec ? a.lr_vec : a.lr_alpha;
+        update(lr, g4f.x, p4f.x, m4f.x, v4f.x);
+        update(lr, g4f.y, p4f.y, m4f.y, v4f.y);
+        update(lr, g4f.z, p4f.z, m4f.z, v4f.z);
+        update(lr, g4f.w, p4f.w, m4f.w, v4f.w);
+        reinterpret_cast<float4*>(a.p)[gtid] = p4f;
+        reinterpret_cast<float4*>(a.m)[gtid] = m4f;
+        reinterpret_cast<float4*>(a.v)[gtid] = v4f;
+    }
+    for (int64_t i4 = gtid + gstride; i4 < n4; i4 += gstride) {
         const float lr = i4 * 4 < a.n_vec ? a.lr_vec : a.lr_alpha;
         const float4 g4 = reinterpret_cast<const float4*>(a.g)[i4];
         float4 p4 = reinterpret_cast<float4*>(a.p)[i4];

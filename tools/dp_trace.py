@@ -11,6 +11,9 @@ import ctypes
 import os
 import sys
 
+# the trace points live in the all-to-all form of the kernel (the owner form is the default)
+os.environ.setdefault("LICV_DP_ALGO", "all")
+
 import numpy as np
 import torch
 

@@ -101,125 +101,27 @@ icv_scale_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ 
 }
 
 // The tail of a backward pass in ONE launch (reduce_rows + icv_scale_bwd + the optimizer's sum of
-// squares): one CTA per layer, one thread per four columns.  d_icv = sum of the replicas the
-// spread backward launches left (zero-filled again if `clear`), d_vec (+)= alpha_eff * d_icv,
-// d_alpha (+)= (d_icv . vec) * dsigmoid, partial[l] = |prescale * (d_vec row, d_alpha)|^2 of the
-// STORED values, summed in a fixed order (shuffle butterfly, then the warps in index order).
-__global__ void __launch_bounds__(1024, 1)
-icv_grad_finish_kernel(float* __restrict__ rows, int n_rows, int64_t layer_stride,
-                       const float* __restrict__ alpha, const float* __restrict__ vec,
-                       float* __restrict__ d_icv, float* __restrict__ d_vec,
-                       float* __restrict__ d_alpha, float* __restrict__ partial, float prescale,
-                       int d, int use_sigmoid, int accumulate, int clear) {
-    pdl_launch_dependents();
-    const int l = blockIdx.x;
-    const int d4 = d / 4;
-    // the parameters are last step's: hint this thread's share into L2 ahead of the wait
-    if ((threadIdx.x & 7) == 0 && (int)threadIdx.x < d4) prefetch_l2(vec + (int64_t)l * d + threadIdx.x * 4);
-    pdl_wait();
-    __shared__ float slab[2][32];
-    float a = alpha[l];
-    float da = 1.0f;
-    if (use_sigmoid) {
-        a = sigmoidf(a);
-        da = a * (1.0f - a);
-    }
-    const float4* v4 = reinterpret_cast<const float4*>(vec + (int64_t)l * d);
-    float4* o4 = reinterpret_cast<float4*>(d_vec + (int64_t)l * d);
-    float dot = 0.f, ss = 0.f;
-    for (int i = threadIdx.x; i < d4; i += blockDim.x) {
-        float4* src = reinterpret_cast<float4*>(rows + l * layer_stride) + i;
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        int p = 0;
-        for (; p + 8 <= n_rows; p += 8) {
-            float4 r[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) r[u] = __ldcg(src + (int64_t)(p + u) * d4);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                g.x += r[u].x; g.y += r[u].y; g.z += r[u].z; g.w += r[u].w;
-            }
-        }
-        for (; p < n_rows; ++p) {
-            const float4 r = __ldcg(src + (int64_t)p * d4);
-            g.x += r.x; g.y += r.y; g.z += r.z; g.w += r.w;
-        }
-        if (clear) {   // the replicas are ready for the next backward pass
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = 0; q < n_rows; ++q) src[(int64_t)q * d4] = z;
-        }
-        if (d_icv) reinterpret_cast<float4*>(d_icv + (int64_t)l * d)[i] = g;
-        const float4 v = v4[i];
-        dot = fmaf(g.x, v.x, dot); dot = fmaf(g.y, v.y, dot);
-        dot = fmaf(g.z, v.z, dot); dot = fmaf(g.w, v.w, dot);
-        float4 o = make_float4(a * g.x, a * g.y, a * g.z, a * g.w);
-        if (accumulate) {
-            const float4 old = o4[i];
-            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-        }
-        o4[i] = o;
-        const float s0 = o.x * prescale, s1 = o.y * prescale, s2 = o.z * prescale, s3 = o.w * prescale;
-        ss = fmaf(s0, s0, ss); ss = fmaf(s1, s1, ss); ss = fmaf(s2, s2, ss); ss = fmaf(s3, s3, ss);
-    }
-    if (d_alpha == nullptr && partial == nullptr) return;
-    dot = warp_sum(dot);
-    ss = warp_sum(ss);
-    if ((threadIdx.x & 31) == 0) {
-        slab[0][threadIdx.x >> 5] = dot;
-        slab[1][threadIdx.x >> 5] = ss;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float sd = 0.f, sq = 0.f;
-        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) {
-            sd += slab[0][w];
-            sq += slab[1][w];
-        }
-        if (d_alpha) {
-            float x = sd * da;
-            if (accumulate) x += d_alpha[l];
-            d_alpha[l] = x;
-            x *= prescale;
-            sq = fmaf(x, x, sq);
-        }
-        if (partial) partial[l] = sq;
-    }
-}
+// squares).  d_icv = sum of the replicas the spread backward launches left (zero-filled again if
+// `clear`), d_vec (+)= alpha_eff * d_icv, d_alpha (+)= (d_icv . vec) * dsigmoid, partial[l] =
+// |prescale * (d_vec row, d_alpha)|^2 of the STORED values, summed in a fixed order (shuffle
+// butterfly, the warps in index order, then the CTAs of a layer in index order).
+struct FinishArgs {
+    float* rows; int n_rows; int64_t layer_stride;
+    const float* alpha; const float* vec;
+    float* d_icv; float* d_vec; float* d_alpha; float* partial;
+    float prescale; int d, use_sigmoid, accumulate, clear;
+};
 
-// The same launch for wide layers: a thread-block cluster of kFinishCluster CTAs per layer, CTA c
-// takes the c-th share of the columns (one SM per layer could not pull its 16 replicas x 16 KB
-// out of L2 and zero them fast enough: 10 us for 32 layers), and the CTAs' (dot, sum of squares)
-// meet in CTA 0's shared memory (DSMEM stores, one cluster barrier), added in CTA order.
-constexpr int kFinishCluster = 4;
-__global__ void __launch_bounds__(256)
-icv_grad_finish_cluster_kernel(float* __restrict__ rows, int n_rows, int64_t layer_stride,
-                               const float* __restrict__ alpha, const float* __restrict__ vec,
-                               float* __restrict__ d_icv, float* __restrict__ d_vec,
-                               float* __restrict__ d_alpha, float* __restrict__ partial,
-                               float prescale, int d, int use_sigmoid, int accumulate, int clear) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    pdl_launch_dependents();
-    const int l = blockIdx.x / kFinishCluster, c = blockIdx.x % kFinishCluster;
-    const int d4 = d / 4;
-    const int per = (d4 + kFinishCluster - 1) / kFinishCluster;
-    const int lo = c * per, hi = lo + per < d4 ? lo + per : d4;
-    if ((threadIdx.x & 7) == 0 && lo + (int)threadIdx.x < hi)
-        prefetch_l2(vec + (int64_t)l * d + (lo + threadIdx.x) * 4);
-    pdl_wait();
-    __shared__ float slab[2][8];
-    __shared__ float met[2][kFinishCluster];   // CTA 0's: every CTA's (dot, sum of squares)
-    float a = alpha[l];
-    float da = 1.0f;
-    if (use_sigmoid) {
-        a = sigmoidf(a);
-        da = a * (1.0f - a);
-    }
-    const float4* v4 = reinterpret_cast<const float4*>(vec + (int64_t)l * d);
-    float4* o4 = reinterpret_cast<float4*>(d_vec + (int64_t)l * d);
+// columns [lo, hi) (in float4 units) of layer l, one float4 column per thread and sweep:
+// -> this CTA's (d_icv . vec, sum of squares of the stored d_vec * prescale) in thread 0
+__device__ __forceinline__ float2 finish_columns(const FinishArgs& a, int l, int lo, int hi, float alpha_eff,
+                                                 float (*slab)[32]) {
+    const int d4 = a.d / 4;
+    const float4* v4 = reinterpret_cast<const float4*>(a.vec + (int64_t)l * a.d);
+    float4* o4 = reinterpret_cast<float4*>(a.d_vec + (int64_t)l * a.d);
     float dot = 0.f, ss = 0.f;
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        float4* src = reinterpret_cast<float4*>(rows + l * layer_stride) + i;
+        float4* src = reinterpret_cast<float4*>(a.rows + l * a.layer_stride) + i;
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         // the first 16 replicas (all of them for the shapes licv_inject_bwd_rows answers) in ONE
         // batch of loads: the launch is a chain of L2 round trips, not bandwidth
@@ -228,32 +130,32 @@ icv_grad_finish_cluster_kernel(float* __restrict__ rows, int n_rows, int64_t lay
             float4 r[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u)
-                r[u] = u < n_rows ? __ldcg(src + (int64_t)u * d4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                r[u] = u < a.n_rows ? __ldcg(src + (int64_t)u * d4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
                 g.x += r[u].x; g.y += r[u].y; g.z += r[u].z; g.w += r[u].w;
             }
-            p = n_rows < 16 ? n_rows : 16;
+            p = a.n_rows < 16 ? a.n_rows : 16;
         }
-        for (; p < n_rows; ++p) {
+        for (; p < a.n_rows; ++p) {
             const float4 r = __ldcg(src + (int64_t)p * d4);
             g.x += r.x; g.y += r.y; g.z += r.z; g.w += r.w;
         }
-        if (clear) {
+        if (a.clear) {   // the replicas are ready for the next backward pass
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = 0; q < n_rows; ++q) src[(int64_t)q * d4] = z;
+            for (int q = 0; q < a.n_rows; ++q) src[(int64_t)q * d4] = z;
         }
-        if (d_icv) reinterpret_cast<float4*>(d_icv + (int64_t)l * d)[i] = g;
+        if (a.d_icv) reinterpret_cast<float4*>(a.d_icv + (int64_t)l * a.d)[i] = g;
         const float4 v = v4[i];
         dot = fmaf(g.x, v.x, dot); dot = fmaf(g.y, v.y, dot);
         dot = fmaf(g.z, v.z, dot); dot = fmaf(g.w, v.w, dot);
-        float4 o = make_float4(a * g.x, a * g.y, a * g.z, a * g.w);
-        if (accumulate) {
+        float4 o = make_float4(alpha_eff * g.x, alpha_eff * g.y, alpha_eff * g.z, alpha_eff * g.w);
+        if (a.accumulate) {
             const float4 old = o4[i];
             o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
         }
         o4[i] = o;
-        const float s0 = o.x * prescale, s1 = o.y * prescale, s2 = o.z * prescale, s3 = o.w * prescale;
+        const float s0 = o.x * a.prescale, s1 = o.y * a.prescale, s2 = o.z * a.prescale, s3 = o.w * a.prescale;
         ss = fmaf(s0, s0, ss); ss = fmaf(s1, s1, ss); ss = fmaf(s2, s2, ss); ss = fmaf(s3, s3, ss);
     }
     dot = warp_sum(dot);
@@ -263,15 +165,73 @@ icv_grad_finish_cluster_kernel(float* __restrict__ rows, int n_rows, int64_t lay
         slab[1][threadIdx.x >> 5] = ss;
     }
     __syncthreads();
+    float sd = 0.f, sq = 0.f;
     if (threadIdx.x == 0) {
-        float sd = 0.f, sq = 0.f;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) {
             sd += slab[0][w];
             sq += slab[1][w];
         }
+    }
+    return make_float2(sd, sq);
+}
+
+// thread 0 of the layer's (first) CTA: d_alpha and the layer's squared norm
+__device__ __forceinline__ void finish_layer(const FinishArgs& a, int l, float sd, float sq, float dsig) {
+    if (a.d_alpha) {
+        float x = sd * dsig;
+        if (a.accumulate) x += a.d_alpha[l];
+        a.d_alpha[l] = x;
+        x *= a.prescale;
+        sq = fmaf(x, x, sq);
+    }
+    if (a.partial) a.partial[l] = sq;
+}
+
+__device__ __forceinline__ float2 alpha_eff_of(const FinishArgs& a, int l) {   // (alpha_eff, dsigmoid)
+    float al = a.alpha[l];
+    if (!a.use_sigmoid) return make_float2(al, 1.0f);
+    al = sigmoidf(al);
+    return make_float2(al, al * (1.0f - al));
+}
+
+// one CTA per layer (narrow layers)
+__global__ void __launch_bounds__(1024, 1) icv_grad_finish_kernel(FinishArgs a) {
+    pdl_launch_dependents();
+    const int l = blockIdx.x;
+    const int d4 = a.d / 4;
+    // the parameters are last step's: hint this thread's share into L2 ahead of the wait
+    if ((threadIdx.x & 7) == 0 && (int)threadIdx.x < d4) prefetch_l2(a.vec + (int64_t)l * a.d + threadIdx.x * 4);
+    pdl_wait();
+    __shared__ float slab[2][32];
+    const float2 ae = alpha_eff_of(a, l);
+    const float2 s = finish_columns(a, l, 0, d4, ae.x, slab);
+    if (threadIdx.x == 0) finish_layer(a, l, s.x, s.y, ae.y);
+}
+
+// wide layers: a thread-block cluster of kFinishCluster CTAs per layer, CTA c takes the c-th share
+// of the columns (one SM per layer could not pull its 16 replicas x 16 KB out of L2 and zero them
+// fast enough: 10 us for 32 layers), and the CTAs' (dot, sum of squares) meet in CTA 0's shared
+// memory (DSMEM stores, one cluster barrier), added in CTA order.
+constexpr int kFinishCluster = 4;
+__global__ void __launch_bounds__(256) icv_grad_finish_cluster_kernel(FinishArgs a) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    pdl_launch_dependents();
+    const int l = blockIdx.x / kFinishCluster, c = blockIdx.x % kFinishCluster;
+    const int d4 = a.d / 4;
+    const int per = (d4 + kFinishCluster - 1) / kFinishCluster;
+    const int lo = c * per, hi = lo + per < d4 ? lo + per : d4;
+    if ((threadIdx.x & 7) == 0 && lo + (int)threadIdx.x < hi)
+        prefetch_l2(a.vec + (int64_t)l * a.d + (lo + threadIdx.x) * 4);
+    pdl_wait();
+    __shared__ float slab[2][32];
+    __shared__ float met[2][kFinishCluster];   // CTA 0's: every CTA's (dot, sum of squares)
+    const float2 ae = alpha_eff_of(a, l);
+    const float2 s = finish_columns(a, l, lo, hi, ae.x, slab);
+    if (threadIdx.x == 0) {
         float* dst = cluster.map_shared_rank(&met[0][0], 0);
-        dst[c] = sd;
-        dst[kFinishCluster + c] = sq;
+        dst[c] = s.x;
+        dst[kFinishCluster + c] = s.y;
     }
     cluster.sync();
     if (c == 0 && threadIdx.x == 0) {
@@ -280,14 +240,7 @@ icv_grad_finish_cluster_kernel(float* __restrict__ rows, int n_rows, int64_t lay
             sd += met[0][k];
             sq += met[1][k];
         }
-        if (d_alpha) {
-            float x = sd * da;
-            if (accumulate) x += d_alpha[l];
-            d_alpha[l] = x;
-            x *= prescale;
-            sq = fmaf(x, x, sq);
-        }
-        if (partial) partial[l] = sq;
+        finish_layer(a, l, sd, sq, ae.y);
     }
 }
 
@@ -711,6 +664,12 @@ extern "C" int licv_icv_grad_finish(float* rows, int n_rows, int64_t layer_strid
     if (!alpha_raw || !vec || !d_vec || (n_rows > 0 && !rows)) return LICV_ERR_NULL_POINTER;
     if (!aligned16(rows) || !aligned16(vec) || !aligned16(d_vec) || !aligned16(d_icv))
         return LICV_ERR_MISALIGNED;
+    FinishArgs a;
+    a.rows = rows; a.n_rows = n_rows; a.layer_stride = layer_stride;
+    a.alpha = alpha_raw; a.vec = vec;
+    a.d_icv = d_icv; a.d_vec = d_vec; a.d_alpha = d_alpha_raw; a.partial = norm_partials;
+    a.prescale = grad_prescale; a.d = d; a.use_sigmoid = use_sigmoid;
+    a.accumulate = accumulate; a.clear = clear;
     static const bool cluster_form = [] {
         const char* v = std::getenv("LICV_FINISH_CLUSTER");   // 0: one CTA per layer at any width (A/B)
         return !(v && v[0] == '0');
@@ -723,16 +682,12 @@ extern "C" int licv_icv_grad_finish(float* rows, int n_rows, int64_t layer_strid
         cudaLaunchAttribute attr[2];
         cfg.attrs = attr;
         cfg.numAttrs = launch_attrs(attr, kFinishCluster);
-        return (int)cudaLaunchKernelEx(&cfg, icv_grad_finish_cluster_kernel, rows, n_rows, layer_stride,
-                                       alpha_raw, vec, d_icv, d_vec, d_alpha_raw, norm_partials,
-                                       grad_prescale, d, use_sigmoid, accumulate, clear);
+        return (int)cudaLaunchKernelEx(&cfg, icv_grad_finish_cluster_kernel, a);
     }
     int threads = 256;
     while (threads < 1024 && threads * 4 < d) threads *= 2;
     return launch_pdl(icv_grad_finish_kernel, dim3(n_layers), dim3(threads), 0,
-                      reinterpret_cast<cudaStream_t>(stream), rows, n_rows, layer_stride, alpha_raw, vec,
-                      d_icv, d_vec, d_alpha_raw, norm_partials, grad_prescale, d, use_sigmoid,
-                      accumulate, clear);
+                      reinterpret_cast<cudaStream_t>(stream), a);
 }
 
 extern "C" int licv_get_mask(const int64_t* input_ids, const int64_t* mask_length,

@@ -172,11 +172,14 @@ def test_icv_grad_finish_equals_the_separate_tail(ops, L, R, d, use_sigmoid, acc
     rows32 = host(t_rows)                        # the fp32 replicas the kernel sees (it clears them)
     ops.icv_grad_finish(t_rows, t_alpha, t_vec, d_vec, d_alpha if train_alpha else None, d_icv, partials,
                         grad_prescale=prescale, use_sigmoid=use_sigmoid, accumulate=accumulate)
-    a_eff = 1 / (1 + np.exp(-alpha)) if use_sigmoid else alpha
-    da = a_eff * (1 - a_eff) if use_sigmoid else np.ones(L)
+    # the oracle's autograd of a1 + a2 (pinned to the reference's golden in tests/test_oracle_golden.py)
     want_icv = rows32.sum(1)
-    want_dv = a_eff[:, None] * want_icv + (host(torch.tensor(old_dv, **f32)) if accumulate else 0.0)
-    want_da = (want_icv * host(t_vec)).sum(1) * da + (host(torch.tensor(old_da, **f32)) if accumulate else 0.0)
+    a_eff = O.encoder_alpha(host(t_alpha), use_sigmoid)
+    d_a_eff, want_dv = O.icv_product_bwd(a_eff, host(t_vec), want_icv)
+    want_da = O.encoder_alpha_bwd(host(t_alpha), use_sigmoid, d_a_eff)
+    if accumulate:
+        want_dv = want_dv + host(torch.tensor(old_dv, **f32))
+        want_da = want_da + host(torch.tensor(old_da, **f32))
     assert rel_err(host(d_icv), want_icv) < 1e-6
     assert rel_err(host(d_vec), want_dv) < 1e-6
     if train_alpha:
